@@ -1,0 +1,111 @@
+"""Generate golden vectors for the loss half by running the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` is not on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+It imports ``lib.cov_mixed.Loss_cov_mixed`` and ``lib.nll.pnp_auto`` from
+``/root/reference`` (importable as-is with torch 2.11), feeds them
+the seeded synthetic correspondences of ``lc_b200.synth`` in fp64, and stores
+inputs (rounded to fp32-representable values so the same fixture serves the fp32
+kernel path) plus the reference outputs:
+
+  loss (B,), grads wrt pts3d / pts2d / inv_std, jac (B,6,N,2) = d(update)/d(pts2d),
+  cov (B,6,6) = H^-1, robust weights W and variance estimate sigma (B,N,2).
+
+Nothing under tests/ or the product imports the reference at run time; only
+this script does.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+from lib.cov_mixed import Loss_cov_mixed, clamp_error, robust_weights_cov  # noqa: E402  (reference)
+from lib.nll import pnp_auto  # noqa: E402  (reference)
+from lib import transforms as xforms  # noqa: E402  (reference)
+
+from lc_b200.synth import make_correspondences  # noqa: E402
+
+# name, B, N, seed, valid mode, regime, store_jac
+CASES = [
+    ("b3_n8_s0", 3, 8, 0, "none", "nominal", True),
+    ("b3_n16_s1", 3, 16, 1, "ones", "nominal", True),
+    ("b4_n200_s0", 4, 200, 0, "ones", "nominal", True),
+    ("b4_n200_s2_mask", 4, 200, 2, "mask", "nominal", True),
+    ("b3_n333_s1_init", 3, 333, 1, "ones", "random_init", True),
+    ("b2_n1024_s0", 2, 1024, 0, "ones", "nominal", True),
+    ("b2_n1024_s1_heavy", 2, 1024, 1, "ones", "heavy_outliers", False),
+    ("b1_n4096_s2", 1, 4096, 2, "ones", "nominal", False),
+]
+
+
+def build_inputs(B, N, seed, valid_mode, regime):
+    outlier = 0.30 if regime == "heavy_outliers" else 0.05
+    c = make_correspondences(B, N, seed, outlier_frac=outlier)
+    if regime == "random_init":
+        # what a random-init network emits: near-uniform softmax weights ~1/(2HW) and tiny xyz
+        c.inv_std = c.inv_std * 1e-4
+        c.pts3d = c.pts3d * 0.02
+    if regime == "heavy_outliers":
+        c.pts2d = c.pts2d + 30.0 * (torch.rand(c.pts2d.shape, generator=torch.Generator().manual_seed(seed + 1), dtype=torch.float64) < 0.1)
+    r32 = lambda t: t.to(torch.float32).to(torch.float64)
+    d = dict(K=r32(c.K), pose=r32(c.pose), pts3d=r32(c.pts3d), pts2d=r32(c.pts2d),
+             inv_std=r32(c.inv_std), bbox_3d=r32(c.bbox_3d))
+    # keep the quaternion unit in fp64 after the fp32 rounding? No: the kernel sees the fp32 values.
+    if valid_mode == "none":
+        d["valid"] = None
+    elif valid_mode == "ones":
+        d["valid"] = torch.ones(B, N, dtype=torch.float64)
+    else:
+        g = torch.Generator().manual_seed(seed + 99)
+        d["valid"] = (torch.rand(B, N, generator=g) < 0.7).to(torch.float64)
+    return d
+
+
+def run_reference(d, max_err_len=32, rel_thresh=3, w_e_thresh=4):
+    pts3d = d["pts3d"].clone().requires_grad_(True)
+    pts2d = d["pts2d"].clone().requires_grad_(True)
+    inv_std = d["inv_std"].clone().requires_grad_(True)
+    loss = Loss_cov_mixed(d["K"], d["pose"], pts3d, pts2d, inv_std, d["valid"], bbox_3d=d["bbox_3d"],
+                          max_err_len=max_err_len, rel_thresh=rel_thresh, w_e_thresh=w_e_thresh)
+    g3, g2, gs = torch.autograd.grad(loss.sum(), (pts3d, pts2d, inv_std))
+
+    with torch.no_grad():
+        R, t = xforms.quaternion_rep_to_RT(d["pose"])
+        proj = xforms.project_apply(d["K"], d["pts3d"], R, t)
+        ec = clamp_error(d["pts2d"] - proj, max_err_len)
+        W, sigma = robust_weights_cov(d["inv_std"], ec, d["valid"], rel_thresh=rel_thresh, w_e_thresh=w_e_thresh)
+    jac, cov = pnp_auto.weighted_pnp_jac_wrt_pts2d(proj, d["pose"], d["K"], d["pts3d"], W, with_cov=True)
+    return dict(loss=loss.detach(), g_pts3d=g3, g_pts2d=g2, g_inv_std=gs, W=W, sigma=sigma,
+                jac=jac.detach(), cov=cov.detach())
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    for name, B, N, seed, vmode, regime, store_jac in CASES:
+        d = build_inputs(B, N, seed, vmode, regime)
+        o = run_reference(d)
+        out = {}
+        for k, v in d.items():
+            if v is not None:
+                out["in_" + k] = v.numpy().astype(np.float32)
+        out["has_valid"] = np.array(d["valid"] is not None)
+        for k, v in o.items():
+            if k in ("jac", "W", "sigma") and not store_jac:
+                continue
+            out["ref_" + k] = v.numpy().astype(np.float64)
+        out["params"] = np.array([32.0, 3.0, 4.0])
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: loss={o['loss'].numpy()} -> {os.path.getsize(path)/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()
