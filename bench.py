@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark of the LC hot path (BASELINE.json: "LC fwd+bwd poses/s (B=1024,N=4096)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pipeline p3|p1|p2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one batch of synthetic correspondences:
+  p3 (default, the north-star operator): weighted-PnP LM solve -> LC loss at the solution -> gradients
+      w.r.t. pts3d and inv_std, ONE kernel launch per step (lc_b200.fused.solve_and_loss);
+  p1: LC loss forward+backward only (training semantics, Loss_cov_mixed);  p2: LM solve only.
+Workload at every N: B=1024 poses x N=4096 correspondences PER GPU (weak scaling; the batch shards by
+pose with no data-path collective, the only exchange is the 16-byte all-reduce of the mean loss).
+
+`value`    poses/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`      the same metric through the public API with HOST (pinned) input buffers: per step the H2D copy
+           of K/start/pts3d/pts2d/inv_std/bbox and the D2H read of loss + solved states are inside the
+           timed region (copies overlap the previous step's kernel on a second stream).
+`roofline` HBM: algorithmic bytes per launch (48*N + 228 per pose) / launch time, against the
+           measured copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the CPU oracle (C/OpenMP port of the reference path; the reference's
+           Ceres extension cannot be built here) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, N_PTS = 1024, 4096
+N_ROTATE = 4          # distinct input batches cycled through so every step reads data that is not in L2
+METRIC = "LC fwd+bwd poses/s (B=1024,N=4096)"
+
+
+def algorithmic_bytes_per_pose(pipeline: str, n: int) -> int:
+    # fp32 I/O, each array touched once.
+    if pipeline == "p2":
+        return 28 * n + 104
+    return 48 * n + (228 if pipeline == "p3" else 164)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pipeline", default="p3", choices=["p3", "p1", "p2"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--points", type=int, default=N_PTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port).  The ONLY place bench.py touches oracle/.
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_size(batch: int) -> int:
+    cores = os.cpu_count() or 1
+    return max(8, min(batch, 4 * cores))
+
+
+def run_cpu_port(pipeline: str, n_pts: int, sample: int, steps: int, warmup: int):
+    import torch
+    from lc_b200.synth import make_correspondences
+    from oracle import cpu_oracle
+    cpu_oracle.build()
+    cores = os.cpu_count() or 1
+    c = make_correspondences(sample, n_pts, 10).to(torch.float32)
+    mode = {"p3": 3, "p1": 2, "p2": 1}[pipeline]
+    states = c.start if mode & 1 else c.pose
+    arrs = [t.numpy() for t in (c.K, c.pts3d, c.pts2d, c.inv_std, c.bbox_3d, states)]
+    for _ in range(warmup):
+        cpu_oracle.p3(*arrs, mode=mode, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_oracle.p3(*arrs, mode=mode, threads=cores)
+    dt = (time.perf_counter() - t0) / steps
+    return sample / dt, dt, cores
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thr.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(pipeline: str):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(pipeline)
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"isolated LC op {a.pipeline}: B={a.batch}/GPU x N={a.points} dense correspondences (BASELINE.json configs[1])"
+    config = {"workload": workload, "pipeline": a.pipeline, "batch_per_gpu": a.batch, "points": a.points,
+              "parallelism": f"batch-sharded x{world}",
+              "l2": f"inputs rotate over {N_ROTATE} distinct resident batches ({N_ROTATE}x{a.batch * a.points * 28 / 1e6:.0f} MB) > 126 MB L2"}
+
+    if a.impl == "reference":
+        # The reference's own CPU implementation of the path: its Ceres extension cannot be built in this image, so
+        # this arm times the C/OpenMP oracle port with every host core.  Rank 0 only.
+        if rank != 0:
+            return
+        sample = cpu_sample_size(a.batch)
+        v, dt, cores = run_cpu_port(a.pipeline, a.points, sample, max(1, a.steps), max(0, a.warmup))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "poses/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": 0,
+                "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
+                                 "sample": f"{sample} poses x N={a.points} per step, {a.steps} steps, OpenMP over poses"},
+                "e2e": {"value": v, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lc_b200.synth import make_correspondences, planar_view
+    from lc_b200.fused import solve_and_loss
+    from lc_b200.cov_mixed import loss_fwd_bwd
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200.sharded import global_mean
+    from lc_b200 import _native as nat
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lc_b200 has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.lib()
+
+    B, N = a.batch, a.points
+    # synthetic inputs: distinct seeds per rank and per rotating slot; planar layout as the dense call site gives
+    host, devb = [], []
+    for slot in range(N_ROTATE):
+        c = make_correspondences(B, N, 10 + slot + 100 * rank).to(torch.float32)
+        h = dict(K=c.K, start=c.start, pose=c.pose, pts3d=c.pts3d.transpose(1, 2).contiguous(),
+                 pts2d=c.pts2d.transpose(1, 2).contiguous(), inv_std=c.inv_std.transpose(1, 2).contiguous(), bbox=c.bbox_3d)
+        host.append({k: v.pin_memory() for k, v in h.items()})
+        devb.append({k: v.to(dev) for k, v in h.items()})
+    go = torch.full((B,), 1.0 / (B * world), dtype=torch.float32, device=dev)   # d mean / d loss_b
+
+    def views(d):
+        return d["pts3d"].transpose(1, 2), d["pts2d"].transpose(1, 2), d["inv_std"].transpose(1, 2)
+
+    outs = {}
+
+    def step(d, out):
+        p3, p2, s = views(d)
+        if a.pipeline == "p3":
+            r = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, out=out)
+            loss = r["loss"]
+        elif a.pipeline == "p1":
+            r = loss_fwd_bwd(d["K"], d["pose"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go)
+            loss = r["loss"]
+        else:
+            r = lm_solve(d["K"], p3, p2, s, d["start"], weight_mode=nat.W_INV_STD)
+            loss = r["radius"]
+        m = global_mean(loss) if world > 1 else None   # the path's only exchange: a 16-byte all-reduce
+        return r, m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # preallocate outputs once (p3) so the timed region holds exactly one of OUR kernels per step
+    if a.pipeline == "p3":
+        r0, _ = step(devb[0], None)
+        outs = {k: r0[k] for k in ("states", "radius", "invalid", "iters", "loss", "flags", "g_pts3d", "g_inv_std")}
+    for i in range(max(3, a.warmup)):
+        step(devb[i % N_ROTATE], outs)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(devb[i % N_ROTATE], outs)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * a.steps / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, loss + states out, copies overlapped with compute on a second stream ----
+    e2e = None
+    if not a.no_e2e:
+        copy_stream = torch.cuda.Stream(dev)
+        comp = torch.cuda.current_stream(dev)
+        stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        h_loss = torch.empty(B, dtype=torch.float32).pin_memory()
+        h_state = torch.empty(B, 7, dtype=torch.float32).pin_memory()
+        keys = ("K", "start", "pts3d", "pts2d", "inv_std", "bbox") if a.pipeline != "p1" else ("K", "pose", "pts3d", "pts2d", "inv_std", "bbox")
+        h2d = sum(host[0][k].numel() * 4 for k in keys)
+        d2h = h_loss.numel() * 4 + (h_state.numel() * 4 if a.pipeline != "p1" else 0)
+
+        def upload(i):
+            sl = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[sl])
+                for k in keys:
+                    stage[sl][k].copy_(host[i % N_ROTATE][k], non_blocking=True)
+                ready[sl].record(copy_stream)
+
+        def e2e_loop(n):
+            for sl in range(2):
+                freed[sl].record(comp)
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload(i + 1)
+                comp.wait_event(ready[i % 2])
+                r, _ = step(stage[i % 2], outs)
+                freed[i % 2].record(comp)
+                h_loss.copy_(r["loss"] if a.pipeline != "p2" else r["radius"], non_blocking=True)
+                if a.pipeline != "p1":
+                    h_state.copy_(r["states"], non_blocking=True)
+            comp.synchronize()
+
+        n_e2e = max(5, min(a.steps, 20))
+        e2e_loop(3)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(n_e2e)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * n_e2e / float(tt.item()), "unit": "poses/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": n_e2e,
+               "note": "pinned host inputs -> H2D -> one kernel -> D2H of loss+states; gradients stay on the device (they feed the network backward there)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = B * algorithmic_bytes_per_pose(a.pipeline, N)
+    launch_s = ms * 1e-3 / a.steps
+    achieved = bytes_per_launch / launch_s / 1e9
+    kernel = {"p3": "lc_pose_kernel<float,256,LM|LC>", "p1": "lc_pose_kernel<float,256,LC>", "p2": "lc_pose_kernel<float,256,LM>"}[a.pipeline]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(a.pipeline), "kernel": kernel, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "launch_us": launch_s * 1e6,
+                "note": "the kernel is FP64-pipe bound, not HBM bound (DESIGN.md §Roofline); frac is against the HBM copy peak as BASELINE.json asks"}
+
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        sample = cpu_sample_size(B)
+        v, dt, cores = run_cpu_port(a.pipeline, N, sample, 3, 1)
+        cpu = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} poses x N={N}, 3 timed passes after 1 warm-up, OpenMP over poses ({dt * 1e3:.0f} ms/pass)"}
+
+    line = {"metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps,
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+/*
+ * lc_b200 — C ABI of the B200-native LC hot path (liblc_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers, sizes, element strides and a CUDA stream;
+ * no torch / C++ types.  Every pointer is a DEVICE pointer owned by the caller (the library
+ * never allocates, frees or synchronises); kernels are enqueued on `stream` and the call
+ * returns immediately.  Return value: 0 on success, otherwise the cudaError_t of the failed
+ * launch / a negative LC_E_* code; lc_b200_last_error() gives the text.  Re-entrant.
+ *
+ * What each entry point replaces in the reference (fulliu/lc):
+ *
+ *   lc_b200_lm_solve        pnp_ceres_f32_omp / pnp_ceres_f32    lib/pnp/cxx/ext.h:2-15,
+ *                           (cffi binding)                       lib/pnp/cxx/ceres.cpp:72-177,
+ *                           + the host-side prologue of          lib/pnp/pnp_ceres.py:74-140,
+ *                           cer_solver.solve (icov -> L,         lib/pnp/cer_solver.py:27-53
+ *                           nan_to_num, invalid -> start)
+ *   lc_b200_loss_fwd_bwd    Loss_cov_mixed forward + the         lib/cov_mixed.py:100-150
+ *                           autograd backward it implies         (lib/nll/pnp_auto.py:86-135,
+ *                                                                 lib/nll/pnp_utils.py:82-167)
+ *   lc_b200_solve_loss      cer_solver.solve followed by         test.py:127 + losses.py:383
+ *                           Loss_cov_mixed(pose := solution)     (fused, one launch)
+ *   lc_b200_pnp_jac_cov     weighted_pnp_jac_wrt_pts2d(...,      lib/nll/pnp_auto.py:111-135
+ *                           with_cov=True) forward
+ *   lc_b200_pnp_jac_cov_bwd its double-backward w.r.t. weights   lib/nll/pnp_auto.py:129-134
+ *
+ * Layout: every array is described by an lc_view = base pointer + strides IN ELEMENTS, so the
+ * planar (B,N,C) views the dense call site produces (strides (C*N,1,N), losses.py:142-161),
+ * batch-broadcast grids (stride 0) and contiguous AoS tensors are all consumed without a copy.
+ * `dtype` selects the element type of all floating arrays (LC_F32 or LC_F64); arithmetic is fp64.
+ */
+#ifndef LC_B200_H_
+#define LC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LC_B200_ABI_VERSION 1
+
+enum { LC_F32 = 0, LC_F64 = 1 };
+
+/* error codes (negative; positive values are cudaError_t) */
+enum { LC_OK = 0, LC_E_BADARG = -1, LC_E_DTYPE = -2, LC_E_NULL = -3 };
+
+/* weight interpretation for the solver (cer_solver.py:37-40, test.py:54,95) */
+enum {
+    LC_W_ICOV_DIAG = 0, /* (B,N,2) inverse variances;      L = diag(sqrt(icov))            */
+    LC_W_ICOV_FULL = 1, /* (B,N,2,2) inverse covariances;  L = lower Cholesky factor       */
+    LC_W_INV_STD = 2,   /* (B,N,2) inverse std (loss-half input); icov = inv_std^2          */
+    LC_W_SQRT_L = 3     /* (B,N,2,2) L itself, row-major, element [0][1] ignored (ext.h ABI) */
+};
+
+/* flag bits */
+enum {
+    LC_FLAG_NAN_TO_NUM = 1,        /* solver: torch.nan_to_num on K, pts3d, pts2d, weights, start (cer_solver.py:27-29) */
+    LC_FLAG_TOL_NEEDS_SUCCESS = 2, /* solver: Ceres >= 2.1 "atleast_one_successful_step" guard (see oracle/lm_oracle.c) */
+    LC_FLAG_EXACT_HESSIAN = 4      /* pnp_jac_cov: include the r * d2r term of hessian_6d_elem (pnp_auto.py:59-83)     */
+};
+
+/* per-pose status bits written to `lc_flags` */
+enum { LC_ST_HESS_NOT_SPD = 1, LC_ST_PRIOR_NOT_GOOD = 2, LC_ST_COV_NOT_GOOD = 4 };
+
+typedef struct lc_view {
+    void* ptr;         /* device pointer, may be NULL for optional arrays */
+    int64_t stride[4]; /* element strides: [batch, point-or-row, component-or-col, (col)] */
+} lc_view;
+
+typedef struct lc_args {
+    int32_t abi_version; /* LC_B200_ABI_VERSION */
+    int32_t B;           /* poses */
+    int32_t N;           /* correspondences per pose (padded maximum for ragged batches) */
+    int32_t dtype;       /* LC_F32 | LC_F64 */
+    int32_t flags;       /* LC_FLAG_* */
+    int32_t weight_mode; /* LC_W_* (solver) */
+    int32_t max_iter;    /* solver: max_num_iterations (50) */
+    int32_t reserved0;
+    double function_tolerance; /* solver (1e-6) */
+    double max_err_len;        /* loss: clamp_error (32) */
+    double rel_thresh;         /* loss: robust_weights_cov (3) */
+    double w_e_thresh;         /* loss: robust_weights_cov (4) */
+    double grad_scale;         /* loss: all input gradients are multiplied by grad_scale * grad_out[b] */
+
+    /* inputs */
+    lc_view K;        /* (B,3,3) */
+    lc_view pose;     /* (B,7) wxyz+t: loss operating point / solver start */
+    lc_view pts3d;    /* (B,N,3) */
+    lc_view pts2d;    /* (B,N,2) */
+    lc_view weights;  /* loss: inv_std (B,N,2); solver: see weight_mode; jac: weights (B,N,2) */
+    lc_view valid;    /* (B,N) or NULL */
+    lc_view bbox;     /* (B,8,3) */
+    lc_view grad_out; /* (B) upstream d/d loss_b, or NULL (= 1) */
+    const int32_t* n_points; /* (B) valid correspondences per pose, or NULL (= N) */
+
+    /* outputs (NULL = not wanted) */
+    lc_view loss;      /* (B) */
+    lc_view g_pts3d;   /* (B,N,3) */
+    lc_view g_pts2d;   /* (B,N,2) */
+    lc_view g_weights; /* (B,N,2) d/d inv_std (loss) or d/d weights (jac bwd) */
+    lc_view cov;        /* (B,6,6) prior_update_cov = H^-1 */
+    lc_view update_cov; /* (B,6,6) sym(A diag(sigma) A^T) */
+    lc_view jac;        /* (B,6,N,2) d(update)/d(pts2d) */
+    lc_view g_jac;      /* (B,6,N,2) upstream gradient of jac (jac bwd) */
+    lc_view g_cov;      /* (B,6,6) upstream gradient of cov (jac bwd) or NULL */
+    lc_view state;      /* (B,7) solver result (start where invalid) */
+    lc_view radius;     /* (B) final trust-region radius */
+    int32_t* invalid;   /* (B) solver_invalids */
+    int32_t* iters;     /* (B) LM iterations taken, or NULL */
+    int32_t* lc_flags;  /* (B) LC_ST_* bits, or NULL */
+    double* trace;      /* (B, max_iter+2, 4) [cost, radius, step_ok, gmax] per finalised iteration, or NULL */
+} lc_args;
+
+int lc_b200_abi_version(void);
+const char* lc_b200_last_error(void);
+
+int lc_b200_lm_solve(const lc_args* a, void* cuda_stream);
+int lc_b200_loss_fwd_bwd(const lc_args* a, void* cuda_stream);
+int lc_b200_solve_loss(const lc_args* a, void* cuda_stream);
+int lc_b200_pnp_jac_cov(const lc_args* a, void* cuda_stream);
+int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* cuda_stream);
+
+/* number of kernels the last call on this thread launched (bench.py's gpu_launches claim) */
+int lc_b200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC_B200_H_ */

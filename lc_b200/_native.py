@@ -1,0 +1,168 @@
+"""ctypes binding of the C ABI in ``include/lc_b200.h`` (``liblc_b200.so``).
+
+PyTorch is used here only as plumbing: device memory, the current CUDA stream and
+dtype/stride bookkeeping.  Every call hands raw device pointers + element strides to
+the hand-written sm_100a kernels.  There is NO CPU or PyTorch fallback: if the shared
+library is missing, or the tensors are not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "liblc_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "lc_kernels.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_ROOT, "include", "lc_b200.h")]
+
+ABI_VERSION = 1
+LC_F32, LC_F64 = 0, 1
+W_ICOV_DIAG, W_ICOV_FULL, W_INV_STD, W_SQRT_L = 0, 1, 2, 3
+FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN = 1, 2, 4
+ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
+
+EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
+           "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd")
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class lc_view(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stride", C.c_int64 * 4)]
+
+
+_VIEW_FIELDS = ("K", "pose", "pts3d", "pts2d", "weights", "valid", "bbox", "grad_out")
+_OUT_VIEW_FIELDS = ("loss", "g_pts3d", "g_pts2d", "g_weights", "cov", "update_cov", "jac", "g_jac", "g_cov", "state", "radius")
+
+
+class lc_args(C.Structure):
+    _fields_ = ([("abi_version", C.c_int32), ("B", C.c_int32), ("N", C.c_int32), ("dtype", C.c_int32),
+                 ("flags", C.c_int32), ("weight_mode", C.c_int32), ("max_iter", C.c_int32), ("reserved0", C.c_int32),
+                 ("function_tolerance", C.c_double), ("max_err_len", C.c_double), ("rel_thresh", C.c_double),
+                 ("w_e_thresh", C.c_double), ("grad_scale", C.c_double)]
+                + [(f, lc_view) for f in _VIEW_FIELDS]
+                + [("n_points", C.c_void_p)]
+                + [(f, lc_view) for f in _OUT_VIEW_FIELDS]
+                + [("invalid", C.c_void_p), ("iters", C.c_void_p), ("lc_flags", C.c_void_p), ("trace", C.c_void_p)])
+
+
+def nvcc_command(out: str = LIB_PATH) -> list:
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out] + SOURCES
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the kernels in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    deps = SOURCES + HEADERS
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if force or stale:
+        cmd = nvcc_command()
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True, cwd=_ROOT)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load liblc_b200.so; raise (never fall back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(lc_b200 has no CPU or PyTorch fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name in EXPORTS:
+            if not hasattr(handle, name):
+                raise NativeLibraryError(f"{LIB_PATH} does not export {name}")
+        handle.lc_b200_last_error.restype = C.c_char_p
+        for name in EXPORTS[3:]:
+            getattr(handle, name).argtypes = [C.POINTER(lc_args), C.c_void_p]
+            getattr(handle, name).restype = C.c_int
+        if handle.lc_b200_abi_version() != ABI_VERSION:
+            raise NativeLibraryError("liblc_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return LC_F32
+    if dt == torch.float64:
+        return LC_F64
+    raise TypeError(f"lc_b200 kernels take float32 or float64 tensors, got {dt}")
+
+
+def view_of(t: Optional[torch.Tensor]) -> lc_view:
+    v = lc_view()
+    if t is None:
+        v.ptr = None
+        return v
+    v.ptr = t.data_ptr()
+    st = t.stride()
+    if len(st) > 4:
+        raise ValueError("lc_view supports at most 4 dimensions")
+    for i, s in enumerate(st):
+        v.stride[i] = s
+    return v
+
+
+def check_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NativeLibraryError(
+                "lc_b200 operators run only on CUDA tensors (sm_100a kernels; there is no CPU fallback); "
+                f"got a tensor on {t.device}")
+        dev = dev or t.device
+        if t.device != dev:
+            raise ValueError("all tensors must be on the same CUDA device")
+    return dev
+
+
+def make_args(B: int, N: int, dtype: torch.dtype, **kw) -> lc_args:
+    """Fill an lc_args; tensor-valued keywords become views, int/float keywords are copied."""
+    a = lc_args()
+    a.abi_version = ABI_VERSION
+    a.B, a.N, a.dtype = int(B), int(N), _dtype_code(dtype)
+    a.max_iter = 50
+    a.function_tolerance, a.max_err_len, a.rel_thresh, a.w_e_thresh, a.grad_scale = 1e-6, 32.0, 3.0, 4.0, 1.0
+    for k, v in kw.items():
+        if k in _VIEW_FIELDS or k in _OUT_VIEW_FIELDS:
+            if v is not None and v.dtype != dtype:
+                raise TypeError(f"{k}: expected dtype {dtype}, got {v.dtype}")
+            setattr(a, k, view_of(v))
+        elif k in ("n_points", "invalid", "iters", "lc_flags"):
+            if v is not None and v.dtype != torch.int32:
+                raise TypeError(f"{k} must be int32")
+            setattr(a, k, None if v is None else v.data_ptr())
+        elif k == "trace":
+            if v is not None and v.dtype != torch.float64:
+                raise TypeError("trace must be float64")
+            a.trace = None if v is None else v.data_ptr()
+        else:
+            setattr(a, k, v)
+    return a
+
+
+def call(name: str, args: lc_args, device: torch.device) -> int:
+    """Enqueue one entry point on torch's current stream of `device`; returns the launch count."""
+    handle = lib()
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        rc = getattr(handle, name)(C.byref(args), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {handle.lc_b200_last_error().decode()}")
+    return handle.lc_b200_last_launch_count()

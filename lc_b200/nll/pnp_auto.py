@@ -1,0 +1,100 @@
+"""Implicit differentiation of the weighted-PnP optimum — drop-in for ``lib/nll/pnp_auto.py``.
+
+``weighted_pnp_jac_wrt_pts2d`` (reference ``pnp_auto.py:111-135``) returns
+``jac = d(update)/d(pts2d) = W_k H^-1 J_k`` of shape ``(*, 6, N, 2)`` and, with ``with_cov``,
+``cov = H^-1`` ``(*, 6, 6)``.  The reference builds them from ``(B,N,2,6,6)`` per-coordinate
+Hessians and 6 vmapped ``autograd.grad`` sweeps; here one kernel accumulates the 6x6 Hessian,
+inverts it and writes ``jac`` directly.  Like the reference it is differentiable w.r.t. ``weights``
+(a second kernel implements that backward).
+
+The Hessian is the Gauss-Newton one, ``sum_k W_k J_k J_k^T``; it equals the reference's
+``hessian_6d_elem`` exactly when ``pts2d`` is the re-projection of ``pts3d`` at ``state_gt``
+(residual 0), which is how ``Loss_cov_mixed`` calls it (``cov_mixed.py:120-121``).
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from .. import _native as nat
+
+
+def _weights_as_bn2(weights: Tensor, B: int, N: int) -> Tensor:
+    if weights.dim() >= 2 and weights.shape[-1] == 2 and weights.shape[-2] == 2 and weights.dim() == 4:
+        raise NotImplementedError("full 2x2 weights: the reference's branch (pnp_utils.py:89-92) is not a correct "
+                                  "full-covariance treatment (SURVEY.md §8a) and is not reproduced")
+    if weights.dim() == 2:
+        weights = weights.unsqueeze(-1)
+    return weights.expand(B, N, 2)
+
+
+def _jac_cov_forward(pose, K, pts3d, weights, want_cov=True):
+    dev = nat.check_cuda(pose, K, pts3d, weights)
+    dt = pts3d.dtype
+    B, N = pts3d.shape[:2]
+    jac = torch.empty(B, 6, N, 2, dtype=dt, device=dev)
+    cov = torch.empty(B, 6, 6, dtype=dt, device=dev)
+    flags = torch.empty(B, dtype=torch.int32, device=dev)
+    args = nat.make_args(B, N, dt, K=K.to(dt).expand(B, 3, 3), pose=pose.to(dt).expand(B, 7), pts3d=pts3d,
+                         weights=weights.to(dt), jac=jac, cov=cov, lc_flags=flags)
+    nat.call("lc_b200_pnp_jac_cov", args, dev)
+    return jac, cov, flags
+
+
+class _PnPJacCov(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, pose, K, pts3d):
+        jac, cov, flags = _jac_cov_forward(pose, K, pts3d, weights)
+        ctx.save_for_backward(weights, pose, K, pts3d)
+        ctx.mark_non_differentiable(flags)
+        return jac, cov, flags
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_jac, g_cov, _g_flags):
+        weights, pose, K, pts3d = ctx.saved_tensors
+        dev, dt = pts3d.device, pts3d.dtype
+        B, N = pts3d.shape[:2]
+        gw = torch.empty(B, N, 2, dtype=dt, device=dev)
+        if g_jac is None:
+            g_jac = torch.zeros(B, 6, N, 2, dtype=dt, device=dev)
+        args = nat.make_args(B, N, dt, K=K.to(dt).expand(B, 3, 3), pose=pose.to(dt).expand(B, 7), pts3d=pts3d,
+                             weights=weights.to(dt), g_jac=g_jac.to(dt), g_cov=None if g_cov is None else g_cov.to(dt),
+                             g_weights=gw)
+        nat.call("lc_b200_pnp_jac_cov_bwd", args, dev)
+        return gw.sum_to_size(weights.shape) if gw.shape != weights.shape else gw, None, None, None
+
+
+def weighted_pnp_jac_wrt_pts2d(pts2d: Tensor, state_gt: Tensor, cam_K: Tensor, pts3d: Tensor, weights: Tensor,
+                               with_cov: bool = False):
+    """Reference signature (``pnp_auto.py:111``).  ``pts2d`` is accepted for signature parity; the
+    Gauss-Newton Jacobian does not depend on it (see module docstring)."""
+    batched = pts3d.dim() != 2
+    p3 = pts3d.detach() if batched else pts3d.detach().unsqueeze(0)
+    p3 = p3.reshape((-1,) + tuple(p3.shape[-2:]))
+    B, N = p3.shape[:2]
+    lead = pts3d.shape[:-2]
+    w = weights if batched else weights.unsqueeze(0)
+    w = _weights_as_bn2(w.reshape((B,) + tuple(w.shape[len(lead) if batched else 1:])), B, N)
+    pose = state_gt.detach().reshape(-1, 7).expand(B, 7)
+    K = cam_K.detach().reshape(-1, 3, 3).expand(B, 3, 3)
+    jac, cov, _ = _PnPJacCov.apply(w, pose, K, p3)
+    jac = jac.reshape(lead + (6, N, 2))
+    cov = cov.reshape(lead + (6, 6))
+    return (jac, cov) if with_cov else jac
+
+
+def diff_pnp_perturb(quat_xyz: Tensor, cam_K: Tensor, pts3d: Tensor, pts2d: Tensor, icov2: Tensor, with_cov: bool = True):
+    """Reference signature (``pnp_auto.py:86``): returns ``(info, right_update, cov)``.  ``right_update``
+    is identically zero in value, exactly like the reference's ``nll_update`` (``pnp_utils.py:118-122``);
+    ``info`` is non-zero where the Hessian was not SPD and got replaced by the identity."""
+    jac_cov = weighted_pnp_jac_wrt_pts2d(pts2d, quat_xyz, cam_K, pts3d, icov2, with_cov=True)
+    cov = jac_cov[1]
+    lead = pts3d.shape[:-2]
+    p3 = pts3d.detach().reshape((-1,) + tuple(pts3d.shape[-2:]))
+    B, N = p3.shape[:2]
+    _, _, flags = _jac_cov_forward(quat_xyz.detach().reshape(-1, 7), cam_K.detach().reshape(-1, 3, 3), p3,
+                                   _weights_as_bn2(icov2.detach().reshape((B,) + tuple(icov2.shape[len(lead):])), B, N))
+    info = (flags & nat.ST_HESS_NOT_SPD).reshape(lead)
+    update = cov.new_zeros(lead + (6,))
+    return info, update, (cov if with_cov else None)

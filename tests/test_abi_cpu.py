@@ -1,0 +1,80 @@
+"""CPU: the C-ABI library loads, exports what include/lc_b200.h declares, and the operators fail loudly off-GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from conftest import ROOT
+from lc_b200 import _native as nat
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "lc_b200.h")).read()
+    return sorted(set(re.findall(r"^\s*(?:int|const char\*)\s+(lc_b200_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    nat.build()
+    handle = ctypes.CDLL(nat.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 8
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/lc_b200.h but not exported"
+    assert set(declared) == set(nat.EXPORTS)
+    assert handle.lc_b200_abi_version() == nat.ABI_VERSION
+
+
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of lc_args == the C struct (size and a few offsets), compiled with the host gcc."""
+    c = tmp_path / "sz.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu",'
+                 'sizeof(lc_args),offsetof(lc_args,K),offsetof(lc_args,n_points),offsetof(lc_args,loss),'
+                 'offsetof(lc_args,invalid),offsetof(lc_args,trace));return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
+    exe = tmp_path / "sz"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([gcc, "-o", str(exe), str(c)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    A = nat.lc_args
+    assert got == [ctypes.sizeof(A), A.K.offset, A.n_points.offset, A.loss.offset, A.invalid.offset, A.trace.offset]
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable here."""
+    handle = nat.lib()
+    a = nat.lc_args()
+    a.abi_version = 999
+    assert handle.lc_b200_loss_fwd_bwd(ctypes.byref(a), None) == -1
+    assert b"abi_version" in handle.lc_b200_last_error()
+    assert handle.lc_b200_lm_solve(None, None) == -3
+    a.abi_version = nat.ABI_VERSION
+    a.B, a.N, a.dtype = 4, 8, 7
+    assert handle.lc_b200_loss_fwd_bwd(ctypes.byref(a), None) == -3      # required pointers missing
+    a.B = 0
+    assert handle.lc_b200_loss_fwd_bwd(ctypes.byref(a), None) == 0       # empty batch is a no-op
+    assert handle.lc_b200_last_launch_count() == 0
+
+
+def test_operators_refuse_cpu_tensors():
+    """No CPU / PyTorch fallback: CPU tensors raise instead of silently computing something else."""
+    from lc_b200.cov_mixed import Loss_cov_mixed
+    from lc_b200.pnp import cer_solver
+    from lc_b200.nll import pnp_auto
+    from lc_b200.synth import make_correspondences
+    c = make_correspondences(2, 8, 0).to(torch.float32)
+    with pytest.raises(nat.NativeLibraryError):
+        Loss_cov_mixed(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, bbox_3d=c.bbox_3d)
+    with pytest.raises(nat.NativeLibraryError):
+        cer_solver.solve(c.K, c.pts3d, c.pts2d, c.inv_std ** 2, c.start)
+    with pytest.raises(nat.NativeLibraryError):
+        pnp_auto.weighted_pnp_jac_wrt_pts2d(c.pts2d, c.pose, c.K, c.pts3d, c.inv_std ** 2)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "cpu_oracle" not in txt and "liblc_oracle" not in txt and "import oracle" not in txt, f

@@ -1,0 +1,41 @@
+"""GPU parity of the fused north-star operator (solve -> LC loss at the solution -> gradients) vs the CPU
+oracle pipeline (oracle/p3_oracle.c), and consistency with the two separate operators."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import quat_angle, rel_err
+from lc_b200.synth import make_correspondences, planar_view
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,N,seed", [(8, 16, 0), (6, 200, 1), (4, 1024, 2), (2, 4096, 3)])
+def test_fused_matches_oracle_pipeline(oracle, B, N, seed):
+    from lc_b200.fused import solve_and_loss
+    c = make_correspondences(B, N, seed).to(torch.float32)
+    ref = oracle.p3(c.K, c.pts3d, c.pts2d, c.inv_std, c.bbox_3d, c.start)
+    d = c.to(device="cuda")
+    o = solve_and_loss(d.K, d.start, planar_view(d.pts3d), d.pts2d, planar_view(d.inv_std), None, d.bbox_3d, need=(True, True, True))
+    assert o["launches"] == 1
+    assert np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"]) and np.array_equal(o["iters"].cpu().numpy(), ref["iters"])
+    st = o["states"].cpu().numpy().astype(np.float64)
+    assert quat_angle(st[:, :4], ref["states"][:, :4].astype(np.float64)).max() <= 1e-6
+    assert (np.linalg.norm(st[:, 4:] - ref["states"][:, 4:], axis=1) / np.linalg.norm(ref["states"][:, 4:], axis=1)).max() <= 1e-6
+    assert np.abs(o["loss"].cpu().numpy() - ref["loss"]).max() <= 1e-5 * np.abs(ref["loss"]).max()
+    for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
+        assert rel_err(o[k].cpu().numpy(), ref[k]) <= 1e-4, k
+
+
+def test_fused_equals_solver_then_loss():
+    from lc_b200.fused import solve_and_loss
+    from lc_b200.pnp import cer_solver
+    from lc_b200.cov_mixed import loss_fwd_bwd
+    c = make_correspondences(16, 512, 5).to(torch.float32).to(device="cuda")
+    f = solve_and_loss(c.K, c.start, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d, need=(True, True, True))
+    inv, st = cer_solver.solve(c.K, c.pts3d, c.pts2d, c.inv_std ** 2, c.start)
+    assert torch.equal(f["states"], st) and torch.equal(f["invalid"].bool(), inv["invalids"])
+    l = loss_fwd_bwd(c.K, st, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
+    assert torch.equal(f["loss"], l["loss"])
+    for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
+        assert torch.equal(f[k], l[k])

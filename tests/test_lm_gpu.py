@@ -1,0 +1,122 @@
+"""GPU parity of the solver half: the LM kernel vs the Ceres-faithful CPU restatement (oracle/lm_oracle.c;
+parity with libceres itself is UNPINNED, see its header).  North-star tolerances: rotation <= 1e-6 rad,
+translation <= 1e-6 relative.  The kernel must also reproduce the iteration schedule (iterations, accept
+flags, radii), since the early stop makes the schedule part of the answer."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import quat_angle
+from lc_b200.synth import make_correspondences, planar_view, full_icov_from_inv_std
+
+pytestmark = pytest.mark.gpu
+
+TOL_ROT, TOL_T = 1e-6, 1e-6
+
+
+def _check_states(got, ref, msg=""):
+    ang = quat_angle(got[:, :4].astype(np.float64), ref[:, :4].astype(np.float64))
+    tr = np.linalg.norm(got[:, 4:].astype(np.float64) - ref[:, 4:], axis=1) / np.linalg.norm(ref[:, 4:], axis=1)
+    assert ang.max() <= TOL_ROT, (msg, ang.max())
+    assert tr.max() <= TOL_T, (msg, tr.max())
+
+
+@pytest.mark.parametrize("B,N,seed", [(16, 8, 0), (12, 16, 1), (9, 100, 2), (8, 717, 3), (6, 1849, 4), (4, 4096, 5)])
+def test_lm_matches_oracle_states_and_schedule(oracle, B, N, seed):
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200 import _native as nat
+    c = make_correspondences(B, N, seed).to(torch.float32)
+    icov = c.inv_std ** 2
+    ref = oracle.lm_solve(c.K, c.pts3d, c.pts2d, torch.diag_embed(icov.sqrt()), c.start, want_trace=True)
+    d = c.to(device="cuda")
+    o = lm_solve(d.K, d.pts3d, d.pts2d, icov.cuda(), d.start, weight_mode=nat.W_ICOV_DIAG, want_trace=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"])
+    assert np.array_equal(o["iters"].cpu().numpy(), ref["iters"])
+    _check_states(o["states"].cpu().numpy(), ref["states"].astype(np.float64))
+    assert np.allclose(o["radius"].cpu().numpy(), ref["radius"], rtol=1e-5)
+    tg, tr = o["trace"].cpu().numpy(), ref["trace"]
+    m = ~np.isnan(tr)
+    assert np.array_equal(np.isnan(tg), np.isnan(tr))
+    assert np.allclose(tg[m].reshape(-1, 4)[:, :3], tr[m].reshape(-1, 4)[:, :3], rtol=1e-9)   # cost, radius, accepted
+
+
+def test_lm_full_inverse_covariance_and_planar_layout(oracle):
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200 import _native as nat
+    c = make_correspondences(6, 300, 9).to(torch.float32)
+    icov = full_icov_from_inv_std(c.inv_std, 9)
+    L = torch.linalg.cholesky_ex(icov)[0]
+    ref = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, c.start)
+    d = c.to(device="cuda")
+    o = lm_solve(d.K, planar_view(d.pts3d), planar_view(d.pts2d), icov.cuda(), d.start, weight_mode=nat.W_ICOV_FULL)
+    assert np.array_equal(o["iters"].cpu().numpy(), ref["iters"])
+    _check_states(o["states"].cpu().numpy(), ref["states"].astype(np.float64))
+    o2 = lm_solve(d.K, d.pts3d, d.pts2d, L.cuda(), d.start, weight_mode=nat.W_SQRT_L)
+    _check_states(o2["states"].cpu().numpy(), ref["states"].astype(np.float64))
+
+
+def test_cer_solver_contract_ragged_lists_invalid_and_nan(oracle):
+    """cer_solver.solve (cer_solver.py:6-53): ragged lists + n_points, invalid -> start, filter_input_nan,
+    optimal_start, dict keys / dtypes / device."""
+    from lc_b200.pnp import cer_solver
+    c = make_correspondences(5, 40, 13).to(torch.float32)
+    ns = [40, 17, 2, 33, 40]                       # sample 2 has < 3 points -> invalid (ceres.cpp:84-91)
+    d = c.to(device="cuda")
+    p3 = [d.pts3d[i, :n] for i, n in enumerate(ns)]
+    p2 = [d.pts2d[i, :n] for i, n in enumerate(ns)]
+    ic = [(d.inv_std[i, :n] ** 2) for i, n in enumerate(ns)]
+    st = [s for s in d.start]
+    p2[3] = p2[3].clone()
+    p2[3][5, 0] = float("nan")                     # nan_to_num'd to 0 -> an outlier, still solvable
+    inv, states = cer_solver.solve(d.K, p3, p2, ic, st, num_workers=4, filter_input_nan=True)
+    assert set(inv) == {"solver_invalids", "invalids"} and inv["invalids"].dtype == torch.bool
+    assert states.shape == (5, 7) and states.dtype == torch.float32 and states.is_cuda
+    assert inv["invalids"].cpu().tolist() == [False, False, True, False, False]
+    assert torch.equal(states[2], d.start[2])
+    # oracle on the same padded problem
+    P3 = torch.zeros(5, 40, 3); P2 = torch.zeros(5, 40, 2); IC = torch.zeros(5, 40, 2)
+    for i, n in enumerate(ns):
+        P3[i, :n], P2[i, :n], IC[i, :n] = c.pts3d[i, :n], torch.nan_to_num(p2[i].cpu()), c.inv_std[i, :n] ** 2
+    ref = oracle.lm_solve(c.K, P3, P2, torch.diag_embed(IC.sqrt()), c.start, n_points=np.array(ns, np.int32))
+    assert ref["invalid"].tolist() == [0, 0, 1, 0, 0]
+    _check_states(states.cpu().numpy(), ref["states"].astype(np.float64))
+    # optimal_start bypasses the solve (cer_solver.py:33-34)
+    inv0, s0 = cer_solver.solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start, optimal_start=True)
+    assert torch.equal(s0, d.start) and not inv0["invalids"].any() and set(inv0) == {"invalids"}
+    # max_iter_count exhausted -> NO_CONVERGENCE counts as invalid and returns start (ceres.cpp:134)
+    inv1, s1 = cer_solver.solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start, max_iter_count=1)
+    assert inv1["invalids"].all() and torch.equal(s1, d.start)
+
+
+def test_lm_noise_free_recovers_the_pose():
+    from lc_b200.pnp import cer_solver
+    from lc_b200.synth import quat_to_matrix
+    c = make_correspondences(32, 64, 17)
+    R = quat_to_matrix(c.pose[:, :4])
+    P = c.pts3d @ R.mT + c.pose[:, None, 4:]
+    KP = P @ c.K.mT
+    c.pts2d = KP[..., :2] / KP[..., 2:]
+    d = c.to(torch.float64).to(device="cuda")
+    inv, st = cer_solver.solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start)
+    assert not inv["invalids"].any()
+    st = st.cpu().numpy()
+    assert quat_angle(st[:, :4], c.pose.numpy()[:, :4]).max() < 1e-7
+    assert (np.linalg.norm(st[:, 4:] - c.pose.numpy()[:, 4:], axis=1) / np.linalg.norm(c.pose.numpy()[:, 4:], axis=1)).max() < 1e-7
+
+
+def test_headline_size_lm_is_a_fixed_point_and_batch_independent():
+    """B=1024, N=4096: (i) batching does not change a pose's result, (ii) restarting from the returned pose
+    converges immediately-ish and stays within the early-stop gap, (iii) every pose converges."""
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200 import _native as nat
+    B, N = 1024, 4096
+    c = make_correspondences(B, N, 202).to(torch.float32).to(device="cuda")
+    o = lm_solve(c.K, c.pts3d, c.pts2d, c.inv_std, c.start, weight_mode=nat.W_INV_STD)
+    assert (o["invalid"] == 0).all() and int(o["iters"].max()) <= 6
+    sl = slice(100, 104)
+    p = lm_solve(c.K[sl], c.pts3d[sl], c.pts2d[sl], c.inv_std[sl], c.start[sl], weight_mode=nat.W_INV_STD)
+    assert torch.equal(p["states"], o["states"][sl])
+    r = lm_solve(c.K, c.pts3d, c.pts2d, c.inv_std, o["states"], weight_mode=nat.W_INV_STD)
+    ang = quat_angle(r["states"][:, :4].cpu().double().numpy(), o["states"][:, :4].cpu().double().numpy())
+    assert (r["invalid"] == 0).all() and ang.max() < 1e-4 and int(r["iters"].max()) <= 3
