@@ -132,6 +132,19 @@ def check_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
     return dev
 
 
+def empty_like_dense(t: torch.Tensor) -> torch.Tensor:
+    """Uninitialised tensor of t's shape; keeps t's strides when t is dense and non-overlapping (e.g. the
+    planar (B,N,C) views), contiguous otherwise (e.g. stride-0 broadcasts)."""
+    expected = 1
+    for size, stride in sorted(zip(t.shape, t.stride()), key=lambda p: p[1]):
+        if size == 1:
+            continue
+        if stride != expected:
+            return torch.empty(t.shape, dtype=t.dtype, device=t.device)
+        expected *= size
+    return torch.empty_like(t)
+
+
 def make_args(B: int, N: int, dtype: torch.dtype, **kw) -> lc_args:
     """Fill an lc_args; tensor-valued keywords become views, int/float keywords are copied."""
     a = lc_args()

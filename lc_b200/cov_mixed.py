@@ -47,7 +47,7 @@ def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std:
         grad_out = grad_out.to(dt).expand(B)
     loss = torch.empty(B, dtype=dt, device=dev)
     flags = torch.empty(B, dtype=torch.int32, device=dev)
-    dense_like = lambda t: torch.empty_like(t) if t.is_non_overlapping_and_dense() else torch.empty(t.shape, dtype=dt, device=dev)
+    dense_like = nat.empty_like_dense
     g3 = dense_like(pts3d) if need[0] else None
     g2 = dense_like(pts2d) if need[1] else None
     gs = dense_like(inv_std) if need[2] else None

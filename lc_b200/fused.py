@@ -27,8 +27,7 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
     B, N = pts3d.shape[:2]
     o = out or {}
     new = lambda key, *shape, dtype=dt: o[key] if key in o else torch.empty(*shape, dtype=dtype, device=dev)
-    dense_like = lambda key, t: o[key] if key in o else (
-        torch.empty_like(t) if t.is_non_overlapping_and_dense() else torch.empty(t.shape, dtype=dt, device=dev))
+    dense_like = lambda key, t: o[key] if key in o else nat.empty_like_dense(t)
     res = dict(states=new("states", B, 7), radius=new("radius", B), invalid=new("invalid", B, dtype=torch.int32),
                iters=new("iters", B, dtype=torch.int32), loss=new("loss", B), flags=new("flags", B, dtype=torch.int32),
                g_pts3d=dense_like("g_pts3d", pts3d) if need[0] else None,
