@@ -17,13 +17,15 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "liblc_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "lc_kernels.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_ROOT, "include", "lc_b200.h")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "csrc", "lc_pose.cuh"),
+           os.path.join(_ROOT, "include", "lc_b200.h")]
+BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 
 ABI_VERSION = 1
 LC_F32, LC_F64 = 0, 1
 W_ICOV_DIAG, W_ICOV_FULL, W_INV_STD, W_SQRT_L = 0, 1, 2, 3
-FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN = 1, 2, 4
+FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN, FLAG_FORCE_STREAMING = 1, 2, 4, 8
 ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
@@ -53,9 +55,15 @@ class lc_args(C.Structure):
                 + [("invalid", C.c_void_p), ("iters", C.c_void_p), ("lc_flags", C.c_void_p), ("trace", C.c_void_p)])
 
 
-def nvcc_command(out: str = LIB_PATH) -> list:
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out] + SOURCES
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def nvcc_commands(out: str = LIB_PATH):
+    """One `nvcc -c` per translation unit (run in parallel) and the final link."""
+    objs = [os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o") for src in SOURCES]
+    compiles = [["nvcc"] + NVCC_FLAGS + ["-c", "-o", obj, src] for src, obj in zip(SOURCES, objs)]
+    link = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs
+    return compiles, link
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -63,10 +71,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps = SOURCES + HEADERS
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
-        cmd = nvcc_command()
+        os.makedirs(BUILD_DIR, exist_ok=True)
+        compiles, link = nvcc_commands()
+        procs = []
+        for cmd in compiles:
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            procs.append(subprocess.Popen(cmd, cwd=_ROOT))
+        for cmd, pr in zip(compiles, procs):
+            if pr.wait() != 0:
+                raise subprocess.CalledProcessError(pr.returncode, cmd)
         if verbose:
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True, cwd=_ROOT)
+            print(" ".join(link), flush=True)
+        subprocess.run(link, check=True, cwd=_ROOT)
     return LIB_PATH
 
 

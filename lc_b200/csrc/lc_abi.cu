@@ -1,0 +1,72 @@
+// lc_b200 — the C ABI (include/lc_b200.h): argument validation and kernel-path dispatch.
+//
+// Dispatch rule for the per-pose entry points: the shared-memory resident kernel (lc_resident.cu) takes fp32
+// batches with diagonal weights whose correspondences fit in one SM's shared memory; everything else (fp64
+// tensors, full 2x2 weights, tiny or huge N) goes to the streaming kernel (lc_stream.cu).  Both are hand-written
+// sm_100a kernels; there is no library or host fallback.
+#include <cstdio>
+
+#include "lc_pose.cuh"
+
+namespace lc {
+
+static thread_local char g_err[256] = "";
+static thread_local int g_launches = 0;
+
+static int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+static int check_launch(int rc) {
+    ++g_launches;
+    if (rc != 0) return fail(rc, cudaGetErrorString(static_cast<cudaError_t>(rc)));
+    return LC_OK;
+}
+
+static int dispatch_pose(const lc_args* a, int mode, void* stream) {
+    g_launches = 0;
+    if (!a) return fail(LC_E_NULL, "args is NULL");
+    if (a->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (a->B < 0 || a->N < 0) return fail(LC_E_BADARG, "B and N must be non-negative");
+    if (a->B == 0) return LC_OK;
+    if (a->dtype != LC_F32 && a->dtype != LC_F64) return fail(LC_E_DTYPE, "dtype must be LC_F32 or LC_F64");
+    if (!a->K.ptr || !a->pose.ptr || !a->pts3d.ptr || !a->pts2d.ptr || !a->weights.ptr)
+        return fail(LC_E_NULL, "K, pose, pts3d, pts2d and weights are required");
+    if ((mode & MODE_LC) && !a->bbox.ptr) return fail(LC_E_NULL, "bbox is required for the loss");
+    if ((mode & MODE_LM) && a->max_iter < 0) return fail(LC_E_BADARG, "max_iter must be >= 0");
+    if ((mode & MODE_LM) && (a->weight_mode < LC_W_ICOV_DIAG || a->weight_mode > LC_W_SQRT_L)) return fail(LC_E_BADARG, "bad weight_mode");
+    if (mode == (MODE_LM | MODE_LC) && a->weight_mode != LC_W_INV_STD)
+        return fail(LC_E_BADARG, "solve_loss takes inverse std weights (weight_mode = LC_W_INV_STD)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!(a->flags & LC_FLAG_FORCE_STREAMING) && resident_supported(*a, mode)) return check_launch(launch_resident_pose(*a, mode, st));
+    return check_launch(launch_stream_pose(*a, mode, st));
+}
+
+static int dispatch_jac(const lc_args* a, bool bwd, void* stream) {
+    g_launches = 0;
+    if (!a) return fail(LC_E_NULL, "args is NULL");
+    if (a->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (a->B < 0 || a->N < 0) return fail(LC_E_BADARG, "B and N must be non-negative");
+    if (a->B == 0) return LC_OK;
+    if (a->dtype != LC_F32 && a->dtype != LC_F64) return fail(LC_E_DTYPE, "dtype must be LC_F32 or LC_F64");
+    if (!a->K.ptr || !a->pose.ptr || !a->pts3d.ptr || !a->weights.ptr) return fail(LC_E_NULL, "K, pose, pts3d and weights are required");
+    if (bwd && (!a->g_jac.ptr || !a->g_weights.ptr)) return fail(LC_E_NULL, "g_jac and g_weights are required");
+    return check_launch(launch_stream_jac(*a, bwd, static_cast<cudaStream_t>(stream)));
+}
+
+}  // namespace lc
+
+extern "C" {
+
+int lc_b200_abi_version(void) { return LC_B200_ABI_VERSION; }
+const char* lc_b200_last_error(void) { return lc::g_err; }
+int lc_b200_last_launch_count(void) { return lc::g_launches; }
+
+int lc_b200_lm_solve(const lc_args* a, void* stream) { return lc::dispatch_pose(a, lc::MODE_LM, stream); }
+int lc_b200_loss_fwd_bwd(const lc_args* a, void* stream) { return lc::dispatch_pose(a, lc::MODE_LC, stream); }
+int lc_b200_solve_loss(const lc_args* a, void* stream) { return lc::dispatch_pose(a, lc::MODE_LM | lc::MODE_LC, stream); }
+int lc_b200_pnp_jac_cov(const lc_args* a, void* stream) { return lc::dispatch_jac(a, false, stream); }
+int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatch_jac(a, true, stream); }
+
+}  // extern "C"

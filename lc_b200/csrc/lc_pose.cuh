@@ -1,0 +1,517 @@
+// Per-pose state and the O(1) sections shared by the streaming (lc_stream.cu) and the shared-memory
+// resident (lc_resident.cu) kernels: the Ceres-faithful trust-region logic and the 6x6 forward /
+// reverse algebra of the LC loss.  Math: SURVEY.md §8a / §8c; CPU checkers: oracle/*.c.
+#pragma once
+
+#include <cfloat>
+
+#include "lc_device.cuh"
+
+namespace lc {
+
+enum { MODE_LM = 1, MODE_LC = 2 };
+enum { TERM_CONVERGENCE = 0, TERM_NO_CONVERGENCE = 1, TERM_FAILURE = 2 };
+enum { CTL_EVAL_FULL = 0, CTL_EVAL_COST = 1, CTL_EVAL_JAC = 2, CTL_STOP = 3 };
+
+struct LmState {
+    double x[6], xc[6];        // accepted point / candidate, [angle-axis, t]
+    double A[kSym], gs[6];     // scaled J^T J (packed) and scaled gradient at x
+    double scale[6], diag[6];
+    double cost, cost_c, radius, dec, xnorm, gmax, model_change, reported_radius;
+    double Rm[9], Jl[9], te[3];  // rotation, left Jacobian and translation of the evaluation point
+    int reuse_diag, n_invalid, it, step_ok, any_success, ctl, term, pad;
+};
+
+struct PoseShared {
+    double K[9], pose[7], R[9], Rb[9], t[3], bbox[24];
+    double Tm[36];  // accumulation basis -> reference (right-perturbation) basis: J_ref = J_acc . Tm
+    double red[kMaxWarps * 48];
+    double fin[48];
+    double H[36], G[36], C[36], M[36], T1[36], T2[36], Cbar[36], Mbar[36], Gbar[36], Hbar[36];
+    double bv[6], dth[6], dthbar[6], bbar[6];
+    double rows[24 * 6], vC[24], vM[24], u[24];
+    double wC[8], wM[8], wU[8];
+    double cHL[kSym], cGL[kSym], bL[6];  // reverse-pass coefficients, left basis, packed (off-diagonals doubled)
+    int flag, pad;
+    LmState lm;
+};
+
+// acc[OFF .. OFF+21) += w * J J^T (packed upper)
+template <int OFF, int V, typename F>
+__device__ __forceinline__ void acc_outer(F (&acc)[V], F w, const F (&J)[6]) {
+    F wJ[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) wJ[i] = w * J[i];
+    int k = OFF;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+            acc[k] = fma(wJ[i], J[j], acc[k]);
+            ++k;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// basis changes with T = blockdiag(Rm, I3)
+// ---------------------------------------------------------------------------------------------
+// (T^T S T)_rc for packed-symmetric S
+__device__ inline double tts_entry(const double* Sp, const double* Rm, int r, int c) {
+    auto S = [&](int i, int j) { return Sp[i <= j ? sym_idx(i, j) : sym_idx(j, i)]; };
+    if (r >= 3 && c >= 3) return S(r, c);
+    if (r < 3 && c >= 3) return Rm[r] * S(0, c) + Rm[3 + r] * S(1, c) + Rm[6 + r] * S(2, c);
+    if (r >= 3 && c < 3) return Rm[c] * S(r, 0) + Rm[3 + c] * S(r, 1) + Rm[6 + c] * S(r, 2);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double w = Rm[c] * S(i, 0) + Rm[3 + c] * S(i, 1) + Rm[6 + c] * S(i, 2);
+        s = fma(Rm[i * 3 + r], w, s);
+    }
+    return s;
+}
+// (T M T^T)_rc for a full 6x6 M
+__device__ inline double tmt_entry(const double* M, const double* Rm, int r, int c) {
+    if (r >= 3 && c >= 3) return M[r * 6 + c];
+    if (r < 3 && c >= 3) return Rm[r * 3] * M[c] + Rm[r * 3 + 1] * M[6 + c] + Rm[r * 3 + 2] * M[12 + c];
+    if (r >= 3 && c < 3) return Rm[c * 3] * M[r * 6] + Rm[c * 3 + 1] * M[r * 6 + 1] + Rm[c * 3 + 2] * M[r * 6 + 2];
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double w = Rm[c * 3] * M[i * 6] + Rm[c * 3 + 1] * M[i * 6 + 1] + Rm[c * 3 + 2] * M[i * 6 + 2];
+        s = fma(Rm[r * 3 + i], w, s);
+    }
+    return s;
+}
+
+// general 6x6 basis matrix Tm (row-major): (Tm^T S Tm)_rc for packed-symmetric S, (Tm M Tm^T)_rc for full M
+__device__ inline double tts_gen(const double* Sp, const double* Tm, int r, int c) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w = fma(Sp[i <= j ? sym_idx(i, j) : sym_idx(j, i)], Tm[j * 6 + c], w);
+        s = fma(Tm[i * 6 + r], w, s);
+    }
+    return s;
+}
+__device__ inline double tmt_gen(const double* M, const double* Tm, int r, int c) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double w = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) w = fma(M[i * 6 + j], Tm[c * 6 + j], w);
+        s = fma(Tm[r * 6 + i], w, s);
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LM: Ceres 2.1.0 TrustRegionMinimizer + LevenbergMarquardtStrategy (spec: oracle/lm_oracle.c header)
+// ---------------------------------------------------------------------------------------------
+__device__ inline void lm_set_eval_point(LmState& L, const double* x) {
+    // ceres/rotation.h AngleAxisRotatePoint as a matrix, and the left Jacobian of SO(3):
+    //   d(R(w) X)/dw = -[R X]x Jl(w)
+    const double w0 = x[0], w1 = x[1], w2 = x[2];
+    const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+    double a, bq, cq;  // R = I + a [w]x + bR [w]x^2 ; Jl = I + bq [w]x + cq [w]x^2
+    const bool big = th2 > DBL_EPSILON;
+    if (big) {
+        const double th = sqrt(th2);
+        double sn, cs;
+        sincos(th, &sn, &cs);
+        a = sn / th;
+        if (th2 > 1e-6) {
+            bq = (1.0 - cs) / th2;
+            cq = (th - sn) / (th2 * th);
+        } else {
+            bq = 0.5 - th2 / 24.0;
+            cq = 1.0 / 6.0 - th2 / 120.0;
+        }
+    } else {
+        a = 1.0; bq = 0.0; cq = 0.0;  // R = I + [w]x (first-order branch of AngleAxisRotatePoint)
+    }
+    const double bR = big ? bq : 0.0;
+    const double W[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double w2rc = W[r * 3] * W[c] + W[r * 3 + 1] * W[3 + c] + W[r * 3 + 2] * W[6 + c];
+            const double id = (r == c) ? 1.0 : 0.0;
+            L.Rm[r * 3 + c] = id + a * W[r * 3 + c] + bR * w2rc;
+            L.Jl[r * 3 + c] = id + bq * W[r * 3 + c] + cq * w2rc;
+        }
+    L.te[0] = x[3]; L.te[1] = x[4]; L.te[2] = x[5];
+}
+
+// fin[0..21) = S (left basis, packed), fin[21..27) = J'^T r, fin[27] = cost at the evaluation point whose
+// left Jacobian is L.Jl.  Builds the scaled normal matrix / gradient into L.A / L.gs; false if not finite.
+__device__ inline bool lm_take_normal_eq(LmState& L, const double* fin, bool first) {
+    double JtJ[kSym], g[6];
+    bool finite = isfinite(fin[27]);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) {
+            const double v = tts_entry(fin, L.Jl, r, c);
+            JtJ[sym_idx(r, c)] = v;
+            finite = finite && isfinite(v);
+        }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) g[r] = L.Jl[r] * fin[21] + L.Jl[3 + r] * fin[22] + L.Jl[6 + r] * fin[23];
+#pragma unroll
+    for (int r = 3; r < 6; ++r) g[r] = fin[21 + r];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) finite = finite && isfinite(g[k]);
+    if (!finite) return false;
+    if (first) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) L.scale[k] = 1.0 / (1.0 + sqrt(JtJ[sym_idx(k, k)]));
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c) L.A[sym_idx(r, c)] = JtJ[sym_idx(r, c)] * L.scale[r] * L.scale[c];
+    double gmax = 0.0, xn = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        L.gs[k] = g[k] * L.scale[k];
+        // Ceres: |x - Plus(x, -g)|_inf, evaluated in floating point
+        const double xs = __dadd_rn(L.x[k], -g[k]);
+        gmax = fmax(gmax, fabs(__dsub_rn(L.x[k], xs)));
+        xn = fma(L.x[k], L.x[k], xn);
+    }
+    L.gmax = gmax;
+    L.cost = fin[27];
+    L.xnorm = sqrt(xn);
+    return true;
+}
+
+// One thread: consume the evaluation in fin[] (kind = the CTL_EVAL_* that produced it), advance the trust-region
+// loop until the next evaluation is known (L.ctl = CTL_EVAL_*) or the solve has terminated (CTL_STOP).
+//
+// Evaluation scheduling (not part of the Ceres semantics, only of how the work is ordered): a FULL evaluation
+// returns cost + normal equations of the candidate in one pass, speculating that the step will be accepted.
+// When the model predicts a cost change below ~2x the function tolerance the candidate is almost surely the
+// converging (discarded) one, so only its COST is evaluated; in the rare case it is then accepted after all,
+// a JAC evaluation at the same point follows.
+__device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool first, int max_iter, double ftol,
+                                  bool tol_guard, double* trace) {
+    const double gtol = 1e-10, ptol = 1e-8, min_rel_dec = 1e-3;
+    const double min_radius = 1e-32, max_radius = 1e16, min_diag = 1e-6, max_diag = 1e32;
+    if (first) {
+        L.radius = 1e4; L.dec = 2.0; L.reuse_diag = 0; L.n_invalid = 0; L.it = 0; L.any_success = 0;
+        L.reported_radius = L.radius; L.term = TERM_FAILURE; L.model_change = 0.0;
+        if (!lm_take_normal_eq(L, fin, true)) { L.ctl = CTL_STOP; return; }
+        L.step_ok = 1;
+    } else if (kind == CTL_EVAL_JAC) {
+        // second half of an accepted step whose cost was evaluated alone
+        if (!lm_take_normal_eq(L, fin, false)) { L.term = TERM_FAILURE; L.ctl = CTL_STOP; return; }
+    } else {
+        const double cost_c = isfinite(fin[27]) ? fin[27] : DBL_MAX;
+        const bool armed = !tol_guard || L.any_success;
+        double sn = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { const double d = L.x[k] - L.xc[k]; sn = fma(d, d, sn); }
+        sn = sqrt(sn);
+        if (armed && sn <= ptol * (L.xnorm + ptol)) { L.term = TERM_CONVERGENCE; L.ctl = CTL_STOP; return; }
+        if (armed && fabs(L.cost - cost_c) <= ftol * L.cost) { L.term = TERM_CONVERGENCE; L.ctl = CTL_STOP; return; }
+        const double rho = cost_c >= DBL_MAX ? -DBL_MAX : (L.cost - cost_c) / L.model_change;
+        if (rho > min_rel_dec) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) L.x[k] = L.xc[k];
+            const double t = 2.0 * rho - 1.0;
+            L.radius = fmin(max_radius, L.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+            L.dec = 2.0; L.reuse_diag = 0; L.step_ok = 1; L.any_success = 1;
+            if (kind == CTL_EVAL_COST) { L.ctl = CTL_EVAL_JAC; return; }   // normal equations still missing
+            if (!lm_take_normal_eq(L, fin, false)) { L.term = TERM_FAILURE; L.ctl = CTL_STOP; return; }
+        } else {
+            L.radius = L.radius / L.dec; L.dec *= 2.0; L.reuse_diag = 1; L.step_ok = 0;
+        }
+    }
+    for (;;) {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        L.reported_radius = L.radius;
+        if (trace) { double* tr = trace + 4 * L.it; tr[0] = L.cost; tr[1] = L.radius; tr[2] = L.step_ok; tr[3] = L.gmax; }
+        if (L.it >= max_iter) { L.term = TERM_NO_CONVERGENCE; L.ctl = CTL_STOP; return; }
+        if (L.step_ok && L.gmax <= gtol) { L.term = TERM_CONVERGENCE; L.ctl = CTL_STOP; return; }
+        if (L.radius <= min_radius) { L.term = TERM_CONVERGENCE; L.ctl = CTL_STOP; return; }
+        ++L.it;
+        // LevenbergMarquardtStrategy::ComputeStep; (J^T J + D^2) y = J^T r replaces DENSE_QR on [J; D]
+        if (!L.reuse_diag) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) L.diag[k] = fmin(fmax(L.A[sym_idx(k, k)], min_diag), max_diag);
+        }
+        double dd[6], y[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dd[k] = L.diag[k] / L.radius;
+        bool valid = chol6_solve_packed(L.A, dd, L.gs, y);
+        L.reuse_diag = 1;
+        double mc = 0.0;
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { y[k] = -y[k]; valid = valid && isfinite(y[k]); }
+        }
+        if (valid) {
+            // model_cost_change = -(J s)'(r + J s / 2) = -s'g - s'As/2
+            double sg = 0.0, sAs = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                sg = fma(y[r], L.gs[r], sg);
+                double row = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) row = fma(L.A[r <= c ? sym_idx(r, c) : sym_idx(c, r)], y[c], row);
+                sAs = fma(y[r], row, sAs);
+            }
+            mc = -sg - 0.5 * sAs;
+            valid = mc > 0.0;
+        }
+        if (!valid) {
+            if (++L.n_invalid >= 5) { L.term = TERM_FAILURE; L.ctl = CTL_STOP; return; }
+            L.radius *= 0.5; L.reuse_diag = 1; L.step_ok = 0;  // StepIsInvalid
+            continue;
+        }
+        L.n_invalid = 0;
+        L.model_change = mc;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) L.xc[k] = L.x[k] + y[k] * L.scale[k];
+        lm_set_eval_point(L, L.xc);
+        const bool armed_next = !tol_guard || L.any_success;
+        L.ctl = (armed_next && mc <= 2.0 * ftol * L.cost) ? CTL_EVAL_COST : CTL_EVAL_FULL;
+        return;
+    }
+}
+
+__device__ inline void quat_to_angle_axis(const double* q, double* aa) {
+    const double s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (s2 > 0.0) {
+        const double sn = sqrt(s2), cs = q[0];
+        const double two_theta = 2.0 * ((cs < 0.0) ? atan2(-sn, -cs) : atan2(sn, cs));
+        const double k = two_theta / sn;
+        aa[0] = q[1] * k; aa[1] = q[2] * k; aa[2] = q[3] * k;
+    } else {
+        aa[0] = q[1] * 2.0; aa[1] = q[2] * 2.0; aa[2] = q[3] * 2.0;
+    }
+}
+__device__ inline void angle_axis_to_quat(const double* aa, double* q) {
+    const double th2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+    if (th2 > 0.0) {
+        const double th = sqrt(th2), h = th * 0.5;
+        double sn, cs;
+        sincos(h, &sn, &cs);
+        const double k = sn / th;
+        q[0] = cs; q[1] = aa[0] * k; q[2] = aa[1] * k; q[3] = aa[2] * k;
+    } else {
+        q[0] = 1.0; q[1] = aa[0] * 0.5; q[2] = aa[1] * 0.5; q[3] = aa[2] * 0.5;
+    }
+}
+
+// LM epilogue (thread 0): ceres.cpp:134-144 writes the state back only when valid; cer_solver.py:51-52 keeps
+// `start` otherwise.  s.pose becomes the pose the LC phase runs at (rounded to the I/O type like the reference).
+template <typename T>
+__device__ inline void lm_write_result(const lc_args& a, PoseShared& s, int b, int n, bool solved) {
+    LmState& L = s.lm;
+    if (solved) {
+        double q[4];
+        angle_axis_to_quat(L.x, q);
+        for (int k = 0; k < 4; ++k) s.pose[k] = static_cast<double>(static_cast<T>(q[k]));
+        for (int k = 0; k < 3; ++k) s.pose[4 + k] = static_cast<double>(static_cast<T>(L.x[3 + k]));
+    }
+    if (a.state.ptr)
+        for (int k = 0; k < 7; ++k) st<T>(a.state, b * a.state.stride[0] + k * a.state.stride[1], s.pose[k]);
+    if (a.radius.ptr) st<T>(a.radius, b * a.radius.stride[0], n >= 3 ? L.reported_radius : 1.0);
+    if (a.invalid) a.invalid[b] = solved ? 0 : 1;
+    if (a.iters) a.iters[b] = n >= 3 ? L.it : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LC loss: pose setup and the 6x6 sections
+// ---------------------------------------------------------------------------------------------
+// `decouple_depth`: the accumulation basis also replaces the t_z column by t_z + (t_x/t_z) t_x + (t_y/t_z) t_y
+// (see lc_resident.cu: keeps fp32 sums well conditioned for objects that are small compared to their depth).
+__device__ inline void lc_pose_setup(PoseShared& s, bool decouple_depth) {   // one thread
+    double qn;
+    quat_to_R_ref(s.pose, s.R, &qn);
+    // derivative of the reference's quaternion_to_matrix(q (x) dq) wrt the right perturbation: n * R_true
+    for (int k = 0; k < 9; ++k) { const double id = (k % 4 == 0) ? 1.0 : 0.0; s.Rb[k] = qn * id + (s.R[k] - id); }
+    s.t[0] = s.pose[4]; s.t[1] = s.pose[5]; s.t[2] = s.pose[6];
+    s.flag = 0;
+    // Tm = blockdiag(R, Ut^-1), Ut^-1 = [[1,0,-uc],[0,1,-vc],[0,0,1]]
+    for (int k = 0; k < 36; ++k) s.Tm[k] = 0.0;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) s.Tm[r * 6 + c] = s.R[r * 3 + c];
+    s.Tm[3 * 6 + 3] = 1.0; s.Tm[4 * 6 + 4] = 1.0; s.Tm[5 * 6 + 5] = 1.0;
+    if (decouple_depth) {
+        s.Tm[3 * 6 + 5] = -s.t[0] / s.t[2];
+        s.Tm[4 * 6 + 5] = -s.t[1] / s.t[2];
+    }
+}
+
+// Forward 6x6 section.  In: s.fin[0..48) = H', G' (packed, left basis), b'.  Out: loss written, s.C, s.M, reverse
+// weights; returns after a barrier.  Follows cov_mixed.py:120-149 on the reference's (right-basis) quantities.
+template <typename T, int NT>
+__device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, int b) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 36; e += NT) {
+        const int r = e / 6, c = e % 6;
+        s.H[e] = tts_gen(s.fin, s.Tm, r, c);
+        s.G[e] = tts_gen(s.fin + 21, s.Tm, r, c);
+    }
+    if (tid < 6) {
+        double v = 0.0;
+        for (int i = 0; i < 6; ++i) v = fma(s.Tm[i * 6 + tid], s.fin[42 + i], v);   // bv = Tm^T b'
+        s.bv[tid] = v;
+    }
+    // bbox corner Jacobian rows [Rb(-[c_j]x) | I]  (cov_mixed.py:52-65)
+    if (tid < 24) {
+        const int j = tid / 3, r = tid % 3;
+        const double* c = s.bbox + 3 * j;
+        const double nC[9] = {0, c[2], -c[1], -c[2], 0, c[0], c[1], -c[0], 0};
+        for (int cc = 0; cc < 3; ++cc) {
+            s.rows[tid * 6 + cc] = s.Rb[r * 3] * nC[cc] + s.Rb[r * 3 + 1] * nC[3 + cc] + s.Rb[r * 3 + 2] * nC[6 + cc];
+            s.rows[tid * 6 + 3 + cc] = (r == cc) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // safe_cholesky: non-SPD -> identity (pnp_utils.py:140-167)
+        double Hs[36];
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) Hs[r * 6 + c] = 0.5 * (s.H[r * 6 + c] + s.H[c * 6 + r]);
+        if (chol6_inverse(Hs, s.C) != 0) {
+            s.flag |= LC_ST_HESS_NOT_SPD;
+            for (int k = 0; k < 36; ++k) s.C[k] = (k % 7 == 0) ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    mm6_par<NT>(s.C, s.G, s.T1);
+    if (tid < 6) {
+        double v = 0.0;
+        for (int k = 0; k < 6; ++k) v = fma(s.C[tid * 6 + k], s.bv[k], v);
+        s.dth[tid] = v;
+    }
+    __syncthreads();
+    mm6_par<NT>(s.T1, s.C, s.M);  // M = C G C
+    __syncthreads();
+    if (tid < 24) {
+        const double* row = s.rows + tid * 6;
+        double vc = 0.0, vm = 0.0, uu = 0.0;
+        for (int r = 0; r < 6; ++r) {
+            double wc = 0.0, wm = 0.0;
+            for (int c = 0; c < 6; ++c) { wc = fma(s.C[r * 6 + c], row[c], wc); wm = fma(s.M[r * 6 + c], row[c], wm); }
+            vc = fma(row[r], wc, vc); vm = fma(row[r], wm, vm); uu = fma(row[r], s.dth[r], uu);
+        }
+        s.vC[tid] = vc; s.vM[tid] = vm; s.u[tid] = uu;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bool goodC = true, goodM = true;
+        for (int k = 0; k < 24; ++k) { goodC = goodC && (s.vC[k] > 0.0); goodM = goodM && (s.vM[k] > 0.0); }
+        double prior = 0.0, cov_err = 0.0, lin = 0.0, sC[8], sM[8], un[8];
+        for (int j = 0; j < 8; ++j) {
+            sC[j] = s.vC[3 * j] + s.vC[3 * j + 1] + s.vC[3 * j + 2];
+            sM[j] = s.vM[3 * j] + s.vM[3 * j + 1] + s.vM[3 * j + 2];
+            un[j] = sqrt(s.u[3 * j] * s.u[3 * j] + s.u[3 * j + 1] * s.u[3 * j + 1] + s.u[3 * j + 2] * s.u[3 * j + 2]);
+            prior += sqrt(goodC ? sC[j] : 1.0);
+            cov_err += sqrt(goodM ? sM[j] : 1.0);
+            lin += un[j];
+        }
+        prior *= 0.125; cov_err *= 0.125; lin *= 0.125;
+        const double loss = log(prior) + 0.5 * (cov_err + lin) / prior;
+        if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], loss);
+        if (!goodC) s.flag |= LC_ST_PRIOR_NOT_GOOD;
+        if (!goodM) s.flag |= LC_ST_COV_NOT_GOOD;
+        if (a.lc_flags) a.lc_flags[b] = s.flag;
+        const double go = a.grad_scale * (a.grad_out.ptr ? ld<T>(a.grad_out, b * a.grad_out.stride[0]) : 1.0);
+        const double g_p = go * (1.0 / prior - 0.5 * (cov_err + lin) / (prior * prior));
+        const double g_c = go * 0.5 / prior;
+        for (int j = 0; j < 8; ++j) {
+            s.wC[j] = goodC ? g_p / (16.0 * sqrt(sC[j])) : 0.0;
+            s.wM[j] = goodM ? g_c / (16.0 * sqrt(sM[j])) : 0.0;
+            s.wU[j] = un[j] > 0.0 ? g_c * 0.125 / un[j] : 0.0;
+        }
+    }
+    if (a.cov.ptr)
+        for (int e = tid; e < 36; e += NT) st<T>(a.cov, b * a.cov.stride[0] + (e / 6) * a.cov.stride[1] + (e % 6) * a.cov.stride[2], s.C[e]);
+    if (a.update_cov.ptr)
+        for (int e = tid; e < 36; e += NT)
+            st<T>(a.update_cov, b * a.update_cov.stride[0] + (e / 6) * a.update_cov.stride[1] + (e % 6) * a.update_cov.stride[2],
+                  0.5 * (s.M[e] + s.M[(e % 6) * 6 + e / 6]));
+    __syncthreads();
+}
+
+// Reverse 6x6 section: fills s.cHL, s.cGL, s.bL (left basis, symmetrised, off-diagonals doubled,
+// already scaled by grad_scale*grad_out).  Ends with a barrier.
+template <int NT>
+__device__ __forceinline__ void lc_six_backward(PoseShared& s) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 36; e += NT) {
+        const int r = e / 6, c = e % 6;
+        double cb = 0.0, mb = 0.0;
+        for (int k = 0; k < 24; ++k) {
+            const double qq = s.rows[k * 6 + r] * s.rows[k * 6 + c];
+            cb = fma(s.wC[k / 3], qq, cb);
+            mb = fma(s.wM[k / 3], qq, mb);
+        }
+        s.Cbar[e] = cb; s.Mbar[e] = mb;
+    }
+    if (tid < 6) {
+        double v = 0.0;
+        for (int k = 0; k < 24; ++k) v = fma(s.wU[k / 3] * s.u[k], s.rows[k * 6 + tid], v);
+        s.dthbar[tid] = v;
+    }
+    __syncthreads();
+    mm6_par<NT>(s.C, s.Mbar, s.T1);   // C Mbar
+    mm6_par<NT>(s.Mbar, s.C, s.T2);   // Mbar C
+    if (tid < 6) {
+        double v = 0.0;
+        for (int k = 0; k < 6; ++k) v = fma(s.C[tid * 6 + k], s.dthbar[k], v);
+        s.bbar[tid] = v;
+    }
+    __syncthreads();
+    mm6_par<NT>(s.T1, s.C, s.Gbar);   // Gbar = C Mbar C
+    mm6_par<NT>(s.T2, s.G, s.Hbar);   // (Mbar C G), staged in Hbar
+    __syncthreads();
+    for (int e = tid; e < 36; e += NT) {
+        const int r = e / 6, c = e % 6;
+        s.T1[e] = s.Cbar[e] + s.Hbar[e] + s.Hbar[c * 6 + r] + s.dthbar[r] * s.bv[c];  // Cbar total
+    }
+    __syncthreads();
+    mm6_par<NT>(s.C, s.T1, s.T2);
+    __syncthreads();
+    mm6_par<NT>(s.T2, s.C, s.Hbar);   // -Hbar
+    __syncthreads();
+    if (s.flag & LC_ST_HESS_NOT_SPD)
+        for (int e = tid; e < 36; e += NT) s.Hbar[e] = 0.0;   // torch.where(cond, eye, H): no gradient into H
+    __syncthreads();
+    // to the accumulation basis, symmetrised and packed with doubled off-diagonals: J^T S J = sum_{i<=j} c_ij J'_i J'_j
+    for (int e = tid; e < kSym * 2; e += NT) {
+        const bool isG = e >= kSym;
+        const int k = isG ? e - kSym : e;
+        int r = 0, c = 0;
+        for (int i = 0, kk = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j, ++kk)
+                if (kk == k) { r = i; c = j; }
+        const double* Msrc = isG ? s.Gbar : s.Hbar;
+        const double sgn = isG ? 1.0 : -1.0;
+        double v = sgn * tmt_gen(Msrc, s.Tm, r, c);
+        if (r != c) v += sgn * tmt_gen(Msrc, s.Tm, c, r);
+        (isG ? s.cGL : s.cHL)[k] = v;
+    }
+    if (tid < 6) {
+        double v = 0.0;
+        for (int j = 0; j < 6; ++j) v = fma(s.Tm[tid * 6 + j], s.bbar[j], v);   // bL = Tm bbar
+        s.bL[tid] = v;
+    }
+    __syncthreads();
+}
+
+// host-side launch entry points implemented in lc_stream.cu / lc_resident.cu (return cudaError_t as int)
+int launch_stream_pose(const lc_args& a, int mode, cudaStream_t st);
+int launch_stream_jac(const lc_args& a, bool bwd, cudaStream_t st);
+bool resident_supported(const lc_args& a, int mode);
+int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st);
+
+}  // namespace lc

@@ -1,0 +1,446 @@
+// lc_b200 — shared-memory resident sm_100a kernel for the LC hot path (the headline path).
+//
+// One CTA per pose.  The pose's correspondences are read from HBM exactly once, converted to a planar
+// fp32 layout in shared memory (28 B/point: X[3], x[2], w[2]), and every later pass runs out of shared
+// memory; the only other HBM traffic is the gradient write-back.  DRAM bytes = the algorithmic
+// 48*N + O(1) per pose.
+//
+//   LM phase  (MODE & 1): fp64.  Each trust-region iteration is one fused pass (cost + J'^T J' + J'^T r in
+//             the left basis, 28 accumulators/thread) + one multi-value CTA reduction + a single-thread
+//             6x6 step.  The converging iteration evaluates the cost only (lc_pose.cuh: lm_advance).
+//   LC phase  (MODE & 2): pass 1 in fp64 computes the camera-frame point P and the clamped error ec once
+//             (as q = R X) and stores them as fp32 IN PLACE over X and x; passes 2-4 (robust statistics, H/G/b
+//             accumulation, reverse pass) are fp32 per point with per-thread partial sums of <= N/NT terms
+//             that are reduced across the CTA in fp64; the 6x6 algebra is fp64 (lc_pose.cuh).
+//
+// Loss-only launches (MODE == 2) skip the raw staging: pass 1 streams X/x from HBM straight into P/ec
+// (20 B/point of shared memory) and the weights are re-read from L2, so two CTAs fit per SM and one CTA's
+// load / 6x6 sections overlap the other's point passes.
+//
+// Restrictions (anything else takes the streaming kernel): fp32 tensors, diagonal weights, 64 < N <= limit.
+#include <cstdio>
+
+#include "lc_pose.cuh"
+
+namespace lc {
+
+constexpr int kResidentMinN = 65;
+
+__host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
+
+struct ResLayout {
+    float *A0, *A1, *A2;  // X -> P
+    float *B0, *B1;       // x -> ec
+    float *S0, *S1;       // weights (raw staging only)
+};
+
+__device__ __forceinline__ ResLayout res_layout(unsigned char* base, int npad, bool raw) {
+    float* f = reinterpret_cast<float*>(base + ((sizeof(PoseShared) + 15) & ~size_t(15)));
+    ResLayout l;
+    l.A0 = f; l.A1 = f + npad; l.A2 = f + 2 * npad; l.B0 = f + 3 * npad; l.B1 = f + 4 * npad;
+    l.S0 = raw ? f + 5 * npad : nullptr;
+    l.S1 = raw ? f + 6 * npad : nullptr;
+    return l;
+}
+
+static size_t resident_smem_bytes(int n, bool raw) {
+    return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * (raw ? 7 : 5) * static_cast<size_t>(round_up4(n));
+}
+
+__device__ __forceinline__ float ldf(const lc_view& v, int64_t off) { return static_cast<const float*>(v.ptr)[off]; }
+__device__ __forceinline__ void stf(const lc_view& v, int64_t off, float x) { static_cast<float*>(v.ptr)[off] = x; }
+__device__ __forceinline__ float nan_to_num_f(float x) {
+    if (isnan(x)) return 0.f;
+    if (isinf(x)) return x > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    return x;
+}
+
+// One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
+// staged fp32 arrays: cost, and when JAC also J'^T J' and J'^T r in the left basis.
+template <int NT, bool JAC>
+__device__ __forceinline__ void lm_eval_pass_res(PoseShared& s, const ResLayout& l, int n) {
+    const LmState& L = s.lm;
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+    const double k00 = s.K[0], k01 = s.K[1], k10 = s.K[3], k11 = s.K[4], cx = s.K[2], cy = s.K[5];
+    const double R0 = L.Rm[0], R1 = L.Rm[1], R2 = L.Rm[2], R3 = L.Rm[3], R4 = L.Rm[4], R5 = L.Rm[5], R6 = L.Rm[6], R7 = L.Rm[7], R8 = L.Rm[8];
+    const double t0 = L.te[0], t1 = L.te[1], t2 = L.te[2];
+#pragma unroll 1
+    for (int i = threadIdx.x; i < n; i += NT) {
+        const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i];
+        const double px = l.B0[i], py = l.B1[i];
+        const double la = fabsf(l.S0[i]), lc_ = fabsf(l.S1[i]);
+        const double q0 = fma(R0, X0, fma(R1, X1, R2 * X2));
+        const double q1 = fma(R3, X0, fma(R4, X1, R5 * X2));
+        const double q2 = fma(R6, X0, fma(R7, X1, R8 * X2));
+        const double p0 = q0 + t0, p1 = q1 + t1, p2 = q2 + t2;
+        const double iz = fast_rcp(p2);
+        const double up = fma(p0, k00, p1 * k01) * iz, vp = fma(p0, k10, p1 * k11) * iz;
+        const double du = up - (px - cx), dv = vp - (py - cy);
+        const double r0 = du * la, r1 = dv * lc_;
+        acc[27] = fma(r0, r0, fma(r1, r1, acc[27]));
+        if (!JAC) continue;
+        const double a0 = la * iz, a1 = lc_ * iz;
+        double J0[6], J1[6];
+        J0[3] = a0 * k00; J0[4] = a0 * k01; J0[5] = -a0 * up;
+        J1[3] = a1 * k10; J1[4] = a1 * k11; J1[5] = -a1 * vp;
+        J0[0] = fma(q1, J0[5], -q2 * J0[4]); J0[1] = fma(q2, J0[3], -q0 * J0[5]); J0[2] = fma(q0, J0[4], -q1 * J0[3]);
+        J1[0] = fma(q1, J1[5], -q2 * J1[4]); J1[1] = fma(q2, J1[3], -q0 * J1[5]); J1[2] = fma(q0, J1[4], -q1 * J1[3]);
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) {
+                acc[k] = fma(J0[r], J0[c], fma(J1[r], J1[c], acc[k]));
+                ++k;
+            }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[21 + c] = fma(J0[c], r0, fma(J1[c], r1, acc[21 + c]));
+    }
+    acc[27] *= 0.5;
+    block_reduce<28, NT>(acc, s.red, s.fin);
+}
+
+template <int NT, int MODE>
+__global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_kernel(const lc_args a, int npad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool RAW = (MODE & MODE_LM) != 0;
+    PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
+    const ResLayout l = res_layout(smem_raw, npad, RAW);
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
+    const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
+
+    // ---- pose constants ----
+    if (tid < 9) {
+        float v = ldf(a.K, b * a.K.stride[0] + (tid / 3) * a.K.stride[1] + (tid % 3) * a.K.stride[2]);
+        s.K[tid] = sanitize ? nan_to_num_f(v) : v;
+    } else if (tid < 16) {
+        float v = ldf(a.pose, b * a.pose.stride[0] + (tid - 9) * a.pose.stride[1]);
+        s.pose[tid - 9] = sanitize ? nan_to_num_f(v) : v;
+    }
+    if (MODE & MODE_LC) {
+        for (int k = tid; k < 24; k += NT)
+            s.bbox[k] = ldf(a.bbox, b * a.bbox.stride[0] + (k / 3) * a.bbox.stride[1] + (k % 3) * a.bbox.stride[2]);
+    }
+
+    // ---- stage the raw correspondences once (coalesced for the planar layout; any strides accepted) ----
+    if (RAW) {
+        const int64_t o3b = b * a.pts3d.stride[0], o2b = b * a.pts2d.stride[0], owb = b * a.weights.stride[0];
+        for (int i = tid; i < npad; i += NT) {
+            float X0 = 0.f, X1 = 0.f, X2 = 0.f, x0 = 0.f, x1 = 0.f, w0 = 0.f, w1 = 0.f;
+            if (i < n) {
+                const int64_t o3 = o3b + i * a.pts3d.stride[1];
+                X0 = ldf(a.pts3d, o3); X1 = ldf(a.pts3d, o3 + a.pts3d.stride[2]); X2 = ldf(a.pts3d, o3 + 2 * a.pts3d.stride[2]);
+                const int64_t o2 = o2b + i * a.pts2d.stride[1];
+                x0 = ldf(a.pts2d, o2); x1 = ldf(a.pts2d, o2 + a.pts2d.stride[2]);
+                const int64_t ow = owb + i * a.weights.stride[1];
+                w0 = ldf(a.weights, ow); w1 = ldf(a.weights, ow + a.weights.stride[2]);
+                if (sanitize) {
+                    X0 = nan_to_num_f(X0); X1 = nan_to_num_f(X1); X2 = nan_to_num_f(X2);
+                    x0 = nan_to_num_f(x0); x1 = nan_to_num_f(x1); w0 = nan_to_num_f(w0); w1 = nan_to_num_f(w1);
+                }
+                // cer_solver.py:37-38: L = diag(sqrt(icov)).  For LC_W_INV_STD the reference computes
+                // sqrt(fl(s*s)) in fp32, which is exactly |s| (barring overflow/underflow of s*s): kept raw, |.| at use.
+                if (a.weight_mode == LC_W_ICOV_DIAG) { w0 = sqrtf(w0); w1 = sqrtf(w1); }
+            }
+            l.A0[i] = X0; l.A1[i] = X1; l.A2[i] = X2; l.B0[i] = x0; l.B1[i] = x1; l.S0[i] = w0; l.S1[i] = w1;
+        }
+    }
+    __syncthreads();
+
+    // =========================== LM solve (fp64) ===========================
+    if (MODE & MODE_LM) {
+        LmState& L = s.lm;
+        double* trace = a.trace ? a.trace + (int64_t)b * (a.max_iter + 2) * 4 : nullptr;
+        bool solved = false;
+        if (n >= 3) {
+            if (tid == 0) {
+                quat_to_angle_axis(s.pose, L.x);
+                L.x[3] = s.pose[4]; L.x[4] = s.pose[5]; L.x[5] = s.pose[6];
+                lm_set_eval_point(L, L.x);
+                L.ctl = CTL_EVAL_FULL;
+            }
+            __syncthreads();
+            bool first = true;
+            for (;;) {
+                const int kind = L.ctl;
+                if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(s, l, n);
+                else lm_eval_pass_res<NT, true>(s, l, n);
+                if (tid == 0)
+                    lm_advance(L, s.fin, kind, first, a.max_iter, a.function_tolerance, (a.flags & LC_FLAG_TOL_NEEDS_SUCCESS) != 0, trace);
+                first = false;
+                __syncthreads();
+                if (L.ctl == CTL_STOP) break;
+            }
+            solved = L.term == TERM_CONVERGENCE;
+        }
+        if (tid == 0) lm_write_result<float>(a, s, b, n, solved);
+        __syncthreads();
+    }
+    if (!(MODE & MODE_LC)) return;
+
+    // =========================== LC loss ===========================
+    if (tid == 0) lc_pose_setup(s, true);
+    __syncthreads();
+
+    const int64_t o3b = b * a.pts3d.stride[0], o2b = b * a.pts2d.stride[0], owb = b * a.weights.stride[0];
+    const int64_t ovb = a.valid.ptr ? b * a.valid.stride[0] : 0;
+    // pass 1 (fp64): P = R X + t, project_apply + clamp_error once per point; P, ec kept as fp32 in place
+    {
+        const double Lmax = a.max_err_len;
+        const double lim = Lmax - 1e-6, lim2 = lim > 0.0 ? lim * lim : -1.0;   // |e|+1e-6 > Lmax  <=>  |e|^2 > lim2
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            double X0, X1, X2, x0, x1;
+            if (RAW) {
+                X0 = l.A0[i]; X1 = l.A1[i]; X2 = l.A2[i]; x0 = l.B0[i]; x1 = l.B1[i];
+            } else {
+                const int64_t o3 = o3b + i * a.pts3d.stride[1];
+                X0 = ldf(a.pts3d, o3); X1 = ldf(a.pts3d, o3 + a.pts3d.stride[2]); X2 = ldf(a.pts3d, o3 + 2 * a.pts3d.stride[2]);
+                const int64_t o2 = o2b + i * a.pts2d.stride[1];
+                x0 = ldf(a.pts2d, o2); x1 = ldf(a.pts2d, o2 + a.pts2d.stride[2]);
+            }
+            const double q0 = fma(s.R[0], X0, fma(s.R[1], X1, s.R[2] * X2));
+            const double q1 = fma(s.R[3], X0, fma(s.R[4], X1, s.R[5] * X2));
+            const double q2 = fma(s.R[6], X0, fma(s.R[7], X1, s.R[8] * X2));
+            const double P0 = q0 + s.t[0], P1 = q1 + s.t[1], P2 = q2 + s.t[2];
+            const double KP0 = fma(s.K[0], P0, fma(s.K[1], P1, s.K[2] * P2));
+            const double KP1 = fma(s.K[3], P0, fma(s.K[4], P1, s.K[5] * P2));
+            const double KP2 = fma(s.K[6], P0, fma(s.K[7], P1, s.K[8] * P2));
+            const double iz = fast_rcp(KP2 > 0.1 ? KP2 : 0.1);
+            double e0 = fma(-KP0, iz, x0), e1 = fma(-KP1, iz, x1);
+            const double l2 = fma(e0, e0, e1 * e1);
+            if (l2 > lim2) {
+                const double len = sqrt(l2) + 1e-6;
+                const double f = (len - Lmax) / len;
+                e0 = fma(-f, e0, e0);
+                e1 = fma(-f, e1, e1);
+            }
+            const float ec0 = static_cast<float>(e0), ec1 = static_cast<float>(e1);
+            // q = R X is what is cached (not P = q + t): q x D then keeps fp32 relative precision even when |X| << |t|
+            l.A0[i] = static_cast<float>(q0); l.A1[i] = static_cast<float>(q1); l.A2[i] = static_cast<float>(q2);
+            l.B0[i] = ec0; l.B1[i] = ec1;
+            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
+            acc0 = fmaf(v, fabsf(ec0), acc0); acc1 = fmaf(v, fabsf(ec1), acc1); acc2 += v;
+        }
+        double acc[3] = {acc0, acc1, acc2};
+        block_reduce<3, NT>(acc, s.red, s.fin);
+    }
+    const double vcnt = a.valid.ptr ? s.fin[2] : static_cast<double>(n);
+    const float d0 = static_cast<float>(a.rel_thresh * (s.fin[0] / vcnt)), d1 = static_cast<float>(a.rel_thresh * (s.fin[1] / vcnt));
+    __syncthreads();
+    // pass 2 (fp32): q_a = mean valid s^2 sigma
+    {
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            float s0, s1;
+            if (RAW) { s0 = l.S0[i]; s1 = l.S1[i]; }
+            else { const int64_t ow = owb + i * a.weights.stride[1]; s0 = ldf(a.weights, ow); s1 = ldf(a.weights, ow + a.weights.stride[2]); }
+            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
+            const float a0 = fabsf(l.B0[i]), a1 = fabsf(l.B1[i]);
+            const float sg0 = a0 > d0 ? d0 * (2.f * a0 - d0) : a0 * a0;
+            const float sg1 = a1 > d1 ? d1 * (2.f * a1 - d1) : a1 * a1;
+            acc0 = fmaf(v * (s0 * s0), sg0, acc0);
+            acc1 = fmaf(v * (s1 * s1), sg1, acc1);
+        }
+        double acc[2] = {acc0, acc1};
+        block_reduce<2, NT>(acc, s.red, s.fin);
+    }
+    // delta_k = sqrt(we * q_a / (sigma_k + 1e-6)) = sq_a * rsqrt(sigma_k + 1e-6)
+    const float sq0 = static_cast<float>(sqrt((s.fin[0] / vcnt) * a.w_e_thresh)), sq1 = static_cast<float>(sqrt((s.fin[1] / vcnt) * a.w_e_thresh));
+    __syncthreads();
+
+    const float t0 = static_cast<float>(s.t[0]), t1 = static_cast<float>(s.t[1]), t2 = static_cast<float>(s.t[2]);
+    const float k00 = static_cast<float>(s.K[0]), k01 = static_cast<float>(s.K[1]), k10 = static_cast<float>(s.K[3]), k11 = static_cast<float>(s.K[4]);
+    // Depth-decoupled accumulation basis.  For an object that is small compared to its depth every point has nearly
+    // the same normalised image position uv0, so the t_z Jacobian column D_z = -K uv0 / z is nearly a fixed combination
+    // of the t_x, t_y columns and H is ill conditioned (cond ~ (z/size)^2: the depth ambiguity).  The sums are therefore
+    // taken with the column t_z' = t_z + uc t_x + vc t_y, (uc, vc) = t_xy / t_z, whose entries
+    //   D_z + uc D_x + vc D_y = K (uvc - uv0) / z = K (uvc q_z - q_xy) / z^2
+    // are formed from the small vector q directly (no cancellation), and mapped back in fp64 (PoseShared::Tm).
+    const float uc = static_cast<float>(s.t[0] / s.t[2]), vc = static_cast<float>(s.t[1] / s.t[2]);
+
+    // per-point fp32 geometry shared by passes 3 and 4: left-basis Jacobian rows and robust weights
+    auto point_terms = [&](int i, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2], float (&w)[2]) {
+        const float q0 = l.A0[i], q1 = l.A1[i], q2 = l.A2[i];
+        const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
+        ec[0] = l.B0[i]; ec[1] = l.B1[i];
+        if (RAW) { sk[0] = l.S0[i]; sk[1] = l.S1[i]; }
+        else { const int64_t ow = owb + i * a.weights.stride[1]; sk[0] = ldf(a.weights, ow); sk[1] = ldf(a.weights, ow + a.weights.stride[2]); }
+        const float iz = __fdividef(1.f, P2);
+        const float u0 = P0 * iz, v0 = P1 * iz;
+        const float du0 = fmaf(uc, q2, -q0) * iz, dv0 = fmaf(vc, q2, -q1) * iz;   // uvc - uv0
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float ka = c ? k10 : k00, kb = c ? k11 : k01;
+            const float e0 = ka * iz, e1 = kb * iz, e2 = -fmaf(ka, u0, kb * v0) * iz;
+            J[c][0] = fmaf(q1, e2, -q2 * e1);
+            J[c][1] = fmaf(q2, e0, -q0 * e2);
+            J[c][2] = fmaf(q0, e1, -q1 * e0);
+            J[c][3] = e0; J[c][4] = e1; J[c][5] = fmaf(ka, du0, kb * dv0) * iz;
+            const float dc = c ? d1 : d0, sq = c ? sq1 : sq0;
+            const float av = fabsf(ec[c]);
+            sg[c] = av > dc ? dc * (2.f * av - dc) : av * av;
+            del[c] = sq * rsqrtf(sg[c] + 1e-6f);
+            w[c] = sk[c] > del[c] ? del[c] * (2.f * sk[c] - del[c]) : sk[c] * sk[c];
+        }
+    };
+
+    // pass 3 (fp32 partial sums, fp64 CTA reduction): H' = sum W J'J'^T, G' = sum W^2 sigma J'J'^T, b' = sum W ec J'
+    {
+        float acc[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, J, ec, sk, sg, del, w);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                acc_outer<0>(acc, w[c], J[c]);
+                acc_outer<21>(acc, w[c] * w[c] * sg[c], J[c]);
+                const float wb = w[c] * ec[c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[42 + r] = fmaf(wb, J[c][r], acc[42 + r]);
+            }
+        }
+        double accd[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) accd[k] = acc[k];
+        block_reduce<48, NT>(accd, s.red, s.fin);
+    }
+    lc_six_forward<float, NT>(a, s, b);
+    const bool want_grads = a.g_pts3d.ptr || a.g_pts2d.ptr || a.g_weights.ptr;
+    if (!want_grads) return;
+    lc_six_backward<NT>(s);
+
+    // pass 4 (fp32): per-coordinate adjoints and the three input gradients
+    {
+        float cH[kSym], cG[kSym], bL[6];
+#pragma unroll
+        for (int k = 0; k < kSym; ++k) { cH[k] = static_cast<float>(s.cHL[k]); cG[k] = static_cast<float>(s.cGL[k]); }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bL[k] = static_cast<float>(s.bL[k]);
+        const float K0 = static_cast<float>(s.K[0]), K1 = static_cast<float>(s.K[1]), K2 = static_cast<float>(s.K[2]);
+        const float K3 = static_cast<float>(s.K[3]), K4 = static_cast<float>(s.K[4]), K5 = static_cast<float>(s.K[5]);
+        const float K6 = static_cast<float>(s.K[6]), K7 = static_cast<float>(s.K[7]), K8 = static_cast<float>(s.K[8]);
+        float Rf[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
+        const int64_t gwb = b * a.g_weights.stride[0], g2b = b * a.g_pts2d.stride[0], g3b = b * a.g_pts3d.stride[0];
+        for (int i = tid; i < n; i += NT) {
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, J, ec, sk, sg, del, w);
+            float ecb[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float qh = 0.f, qg = 0.f, lb = 0.f;
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    lb = fmaf(J[c][r], bL[r], lb);
+#pragma unroll
+                    for (int cc = r; cc < 6; ++cc) {
+                        const float pp = J[c][r] * J[c][cc];
+                        qh = fmaf(cH[k], pp, qh);
+                        qg = fmaf(cG[k], pp, qg);
+                        ++k;
+                    }
+                }
+                const float Wbar = qh + 2.f * w[c] * sg[c] * qg + ec[c] * lb;
+                const float sigbar = w[c] * w[c] * qg;
+                if (a.g_weights.ptr)
+                    stf(a.g_weights, gwb + i * a.g_weights.stride[1] + c * a.g_weights.stride[2], Wbar * (sk[c] > del[c] ? 2.f * del[c] : 2.f * sk[c]));
+                const float dc = c ? d1 : d0;
+                const float av = fabsf(ec[c]);
+                const float sgn = (ec[c] > 0.f) ? 1.f : ((ec[c] < 0.f) ? -1.f : 0.f);
+                ecb[c] = sigbar * (av > dc ? 2.f * dc : 2.f * av) * sgn;
+                if (a.g_pts2d.ptr) stf(a.g_pts2d, g2b + i * a.g_pts2d.stride[1] + c * a.g_pts2d.stride[2], ecb[c]);
+            }
+            if (a.g_pts3d.ptr) {
+                // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
+                const float P0 = l.A0[i] + t0, P1 = l.A1[i] + t1, P2 = l.A2[i] + t2;
+                const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
+                const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
+                const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
+                const bool act = KP2 >= 0.1f;
+                const float iz = __fdividef(1.f, act ? KP2 : 0.1f);
+                const float pr0 = act ? KP0 * iz : 0.f, pr1 = act ? KP1 * iz : 0.f;   // proj * [z >= 0.1]
+                const float gP0 = (fmaf(-pr0, K6, K0) * ecb[0] + fmaf(-pr1, K6, K3) * ecb[1]) * iz;
+                const float gP1 = (fmaf(-pr0, K7, K1) * ecb[0] + fmaf(-pr1, K7, K4) * ecb[1]) * iz;
+                const float gP2 = (fmaf(-pr0, K8, K2) * ecb[0] + fmaf(-pr1, K8, K5) * ecb[1]) * iz;
+                const int64_t o = g3b + i * a.g_pts3d.stride[1];
+                stf(a.g_pts3d, o, -(Rf[0] * gP0 + Rf[3] * gP1 + Rf[6] * gP2));
+                stf(a.g_pts3d, o + a.g_pts3d.stride[2], -(Rf[1] * gP0 + Rf[4] * gP1 + Rf[7] * gP2));
+                stf(a.g_pts3d, o + 2 * a.g_pts3d.stride[2], -(Rf[2] * gP0 + Rf[5] * gP1 + Rf[8] * gP2));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int g_max_smem = -1;
+
+static int max_optin_smem() {
+    if (g_max_smem < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+            cudaGetLastError();
+            v = 0;
+        }
+        g_max_smem = v;
+    }
+    return g_max_smem;
+}
+
+bool resident_supported(const lc_args& a, int mode) {
+    if (a.dtype != LC_F32 || a.N < kResidentMinN) return false;
+    if ((mode & MODE_LM) && a.weight_mode != LC_W_ICOV_DIAG && a.weight_mode != LC_W_INV_STD) return false;
+    const size_t need = resident_smem_bytes(a.N, (mode & MODE_LM) != 0);
+    return need <= static_cast<size_t>(max_optin_smem());
+}
+
+static int resident_threads_for(int n) {
+    if (n <= 512) return 128;
+    if (n <= 2048) return 256;
+    return 512;
+}
+
+template <int NT, int MODE>
+static int launch_res_t(const lc_args& a, cudaStream_t st) {
+    const size_t smem = resident_smem_bytes(a.N, (MODE & MODE_LM) != 0);
+    static size_t configured = 0;   // per instantiation
+    if (smem > configured) {
+        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_optin_smem()));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = static_cast<size_t>(max_optin_smem());
+    }
+    lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(a.N));
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <int MODE>
+static int launch_res_m(const lc_args& a, cudaStream_t st) {
+    const int nt = resident_threads_for(a.N);
+    if (nt == 128) return launch_res_t<128, MODE>(a, st);
+    if constexpr (MODE == MODE_LC) {
+        return launch_res_t<256, MODE>(a, st);   // loss-only: 2 CTAs of 256 threads per SM (see file header)
+    } else {
+        if (nt == 256) return launch_res_t<256, MODE>(a, st);
+        return launch_res_t<512, MODE>(a, st);
+    }
+}
+
+int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st) {
+    switch (mode) {
+        case MODE_LM: return launch_res_m<MODE_LM>(a, st);
+        case MODE_LC: return launch_res_m<MODE_LC>(a, st);
+        default: return launch_res_m<MODE_LM | MODE_LC>(a, st);
+    }
+}
+
+}  // namespace lc

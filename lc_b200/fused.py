@@ -17,7 +17,7 @@ from . import _native as nat
 def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std: Tensor, valid: Optional[Tensor],
                    bbox_3d: Tensor, *, max_iter_count=50, function_tolerance=1e-6, max_err_len=32.0, rel_thresh=3.0,
                    w_e_thresh=4.0, need=(True, False, True), grad_out: Optional[Tensor] = None, grad_scale=1.0,
-                   tol_needs_success=True, out: Optional[dict] = None):
+                   tol_needs_success=True, out: Optional[dict] = None, force_streaming=False):
     """Returns dict(states, radius, invalid, iters, loss, g_pts3d, g_pts2d, g_inv_std, flags).
 
     ``out`` may carry preallocated output tensors from a previous call (same shapes) to avoid allocation.
@@ -33,7 +33,7 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
                g_pts3d=dense_like("g_pts3d", pts3d) if need[0] else None,
                g_pts2d=dense_like("g_pts2d", pts2d.expand(B, N, 2)) if need[1] else None,
                g_inv_std=dense_like("g_inv_std", inv_std) if need[2] else None)
-    flags = nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0
+    flags = (nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0) | (nat.FLAG_FORCE_STREAMING if force_streaming else 0)
     ftol = float(torch.tensor(function_tolerance, dtype=torch.float32))
     args = nat.make_args(B, N, dt, K=K.to(dt).expand(B, 3, 3), pose=start.to(dt).expand(B, 7), pts3d=pts3d,
                          pts2d=pts2d.to(dt).expand(B, N, 2), weights=inv_std.to(dt),

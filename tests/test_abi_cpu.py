@@ -51,6 +51,8 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert handle.lc_b200_lm_solve(None, None) == -3
     a.abi_version = nat.ABI_VERSION
     a.B, a.N, a.dtype = 4, 8, 7
+    assert handle.lc_b200_loss_fwd_bwd(ctypes.byref(a), None) == -2      # bad dtype
+    a.dtype = nat.LC_F32
     assert handle.lc_b200_loss_fwd_bwd(ctypes.byref(a), None) == -3      # required pointers missing
     a.B = 0
     assert handle.lc_b200_loss_fwd_bwd(ctypes.byref(a), None) == 0       # empty batch is a no-op

@@ -10,13 +10,15 @@ from lc_b200.synth import make_correspondences, planar_view
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("streaming", [False, True], ids=["resident", "streaming"])
 @pytest.mark.parametrize("B,N,seed", [(8, 16, 0), (6, 200, 1), (4, 1024, 2), (2, 4096, 3)])
-def test_fused_matches_oracle_pipeline(oracle, B, N, seed):
+def test_fused_matches_oracle_pipeline(oracle, B, N, seed, streaming):
     from lc_b200.fused import solve_and_loss
     c = make_correspondences(B, N, seed).to(torch.float32)
     ref = oracle.p3(c.K, c.pts3d, c.pts2d, c.inv_std, c.bbox_3d, c.start)
     d = c.to(device="cuda")
-    o = solve_and_loss(d.K, d.start, planar_view(d.pts3d), d.pts2d, planar_view(d.inv_std), None, d.bbox_3d, need=(True, True, True))
+    o = solve_and_loss(d.K, d.start, planar_view(d.pts3d), d.pts2d, planar_view(d.inv_std), None, d.bbox_3d, need=(True, True, True),
+                       force_streaming=streaming)
     assert o["launches"] == 1
     assert np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"]) and np.array_equal(o["iters"].cpu().numpy(), ref["iters"])
     st = o["states"].cpu().numpy().astype(np.float64)

@@ -46,14 +46,16 @@ def test_loss_and_grads_match_reference_golden(name, dt):
     assert (o["flags"].cpu().numpy() == 0).all()
 
 
-@pytest.mark.parametrize("B,N,seed", [(5, 8, 3), (3, 33, 4), (7, 129, 5), (4, 1000, 6), (3, 2049, 7), (2, 4096, 8)])
-def test_loss_matches_oracle_on_seeded_inputs(oracle, B, N, seed):
-    """Ragged sizes around every CTA-size switch point (32/64/128/256 threads) against the CPU oracle."""
+@pytest.mark.parametrize("streaming", [False, True], ids=["resident", "streaming"])
+@pytest.mark.parametrize("B,N,seed", [(5, 8, 3), (3, 33, 4), (7, 129, 5), (5, 513, 9), (4, 1000, 6), (3, 2049, 7), (2, 4096, 8), (2, 7001, 10)])
+def test_loss_matches_oracle_on_seeded_inputs(oracle, B, N, seed, streaming):
+    """Ragged sizes around every CTA-size switch point, through both kernel paths (shared-memory resident
+    fp32-point-math kernel and streaming fp64 kernel), against the CPU oracle."""
     from lc_b200.cov_mixed import loss_fwd_bwd
     c = make_correspondences(B, N, seed).to(torch.float32)
     ref = oracle.lc_loss(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
     d = c.to(device="cuda")
-    o = loss_fwd_bwd(d.K, d.pose, d.pts3d, d.pts2d, d.inv_std, None, d.bbox_3d, want_cov=True)
+    o = loss_fwd_bwd(d.K, d.pose, d.pts3d, d.pts2d, d.inv_std, None, d.bbox_3d, want_cov=True, force_streaming=streaming)
     assert np.abs(o["loss"].cpu().numpy() - ref["loss"]).max() <= 2e-6 * np.abs(ref["loss"]).max()
     for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
         assert rel_err(o[k].cpu().numpy(), ref[k]) <= TOL_GRAD, k

@@ -21,15 +21,16 @@ def _check_states(got, ref, msg=""):
     assert tr.max() <= TOL_T, (msg, tr.max())
 
 
-@pytest.mark.parametrize("B,N,seed", [(16, 8, 0), (12, 16, 1), (9, 100, 2), (8, 717, 3), (6, 1849, 4), (4, 4096, 5)])
-def test_lm_matches_oracle_states_and_schedule(oracle, B, N, seed):
+@pytest.mark.parametrize("streaming", [False, True], ids=["resident", "streaming"])
+@pytest.mark.parametrize("B,N,seed", [(16, 8, 0), (12, 16, 1), (9, 100, 2), (8, 717, 3), (6, 1849, 4), (4, 4096, 5), (3, 6000, 6)])
+def test_lm_matches_oracle_states_and_schedule(oracle, B, N, seed, streaming):
     from lc_b200.pnp.cer_solver import lm_solve
     from lc_b200 import _native as nat
     c = make_correspondences(B, N, seed).to(torch.float32)
     icov = c.inv_std ** 2
     ref = oracle.lm_solve(c.K, c.pts3d, c.pts2d, torch.diag_embed(icov.sqrt()), c.start, want_trace=True)
     d = c.to(device="cuda")
-    o = lm_solve(d.K, d.pts3d, d.pts2d, icov.cuda(), d.start, weight_mode=nat.W_ICOV_DIAG, want_trace=True)
+    o = lm_solve(d.K, d.pts3d, d.pts2d, icov.cuda(), d.start, weight_mode=nat.W_ICOV_DIAG, want_trace=True, force_streaming=streaming)
     torch.cuda.synchronize()
     assert np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"])
     assert np.array_equal(o["iters"].cpu().numpy(), ref["iters"])
@@ -38,7 +39,9 @@ def test_lm_matches_oracle_states_and_schedule(oracle, B, N, seed):
     tg, tr = o["trace"].cpu().numpy(), ref["trace"]
     m = ~np.isnan(tr)
     assert np.array_equal(np.isnan(tg), np.isnan(tr))
-    assert np.allclose(tg[m].reshape(-1, 4)[:, :3], tr[m].reshape(-1, 4)[:, :3], rtol=1e-9)   # cost, radius, accepted
+    # cost, radius, accepted.  The kernel solves the 6x6 normal equations (cond^2) where Ceres / the oracle QR-factorise
+    # [J; D] (cond): for N <= 16 the systems are ill-conditioned enough for that to show at ~1e-9 in the trajectory.
+    assert np.allclose(tg[m].reshape(-1, 4)[:, :3], tr[m].reshape(-1, 4)[:, :3], rtol=1e-9 if N > 16 else 1e-6)
 
 
 def test_lm_full_inverse_covariance_and_planar_layout(oracle):
