@@ -133,44 +133,48 @@ __device__ __forceinline__ void mm6_par(const double* A, const double* B, double
     }
 }
 
-// Lower Cholesky + inverse of an SPD 6x6 (single thread).  Returns 0 on success, else the order of the
-// first non-positive leading minor (LAPACK info).  C = A^-1.
+// 1/a to ~1 ulp without the IEEE division sequence: MUFU.RCP64H seed + two Newton steps (5 issue slots
+// instead of ~14 DFMA-equivalents measured for a correctly rounded division on B200).
+__device__ __forceinline__ double fast_rcp(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Lower Cholesky + inverse of an SPD 6x6 (single thread, everything in registers: packed triangles, constant
+// indices).  Returns 0 on success, else the order of the first non-positive leading minor (LAPACK info).
+// A, C: full row-major 6x6.  C = A^-1.
 __device__ inline int chol6_inverse(const double* A, double* C) {
-    double L[36];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) L[k] = 0.0;
-    double inv_d[6];
+    double L[21], il[6];   // L[i][j], i >= j, stored at sym_idx(j, i)
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double d = A[j * 6 + j];
 #pragma unroll
-        for (int k = 0; k < j; ++k) d = fma(-L[j * 6 + k], L[j * 6 + k], d);
+        for (int k = 0; k < j; ++k) d = fma(-L[sym_idx(k, j)], L[sym_idx(k, j)], d);
         if (!(d > 0.0) || isinf(d)) return j + 1;
-        const double ljj = sqrt(d);
-        const double il = 1.0 / ljj;
-        L[j * 6 + j] = ljj;
-        inv_d[j] = il;
+        il[j] = rsqrt(d);
+        L[sym_idx(j, j)] = d * il[j];
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = A[i * 6 + j];
 #pragma unroll
-            for (int k = 0; k < j; ++k) v = fma(-L[i * 6 + k], L[j * 6 + k], v);
-            L[i * 6 + j] = v * il;
+            for (int k = 0; k < j; ++k) v = fma(-L[sym_idx(k, i)], L[sym_idx(k, j)], v);
+            L[sym_idx(j, i)] = v * il[j];
         }
     }
-    // Li = L^-1 (lower)
-    double Li[36];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) Li[k] = 0.0;
+    double Li[21];         // (L^-1)[r][c], r >= c, stored at sym_idx(c, r)
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        Li[c * 6 + c] = inv_d[c];
+        Li[sym_idx(c, c)] = il[c];
 #pragma unroll
         for (int r = c + 1; r < 6; ++r) {
             double v = 0.0;
 #pragma unroll
-            for (int k = c; k < r; ++k) v = fma(-L[r * 6 + k], Li[k * 6 + c], v);
-            Li[r * 6 + c] = v * inv_d[r];
+            for (int k = c; k < r; ++k) v = fma(-L[sym_idx(k, r)], Li[sym_idx(c, k)], v);
+            Li[sym_idx(c, r)] = v * il[r];
         }
     }
 #pragma unroll
@@ -179,7 +183,7 @@ __device__ inline int chol6_inverse(const double* A, double* C) {
         for (int b = a; b < 6; ++b) {
             double v = 0.0;
 #pragma unroll
-            for (int k = b; k < 6; ++k) v = fma(Li[k * 6 + a], Li[k * 6 + b], v);
+            for (int k = b; k < 6; ++k) v = fma(Li[sym_idx(a, k)], Li[sym_idx(b, k)], v);
             C[a * 6 + b] = v;
             C[b * 6 + a] = v;
         }
@@ -196,9 +200,8 @@ __device__ inline bool chol6_solve_packed(const double* Ap, const double* dd, co
 #pragma unroll
         for (int k = 0; k < j; ++k) d = fma(-L[sym_idx(k, j)], L[sym_idx(k, j)], d);
         if (!(d > 0.0) || isinf(d)) return false;
-        const double ljj = sqrt(d);
-        il[j] = 1.0 / ljj;
-        L[sym_idx(j, j)] = ljj;
+        il[j] = rsqrt(d);
+        L[sym_idx(j, j)] = d * il[j];
 #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = Ap[sym_idx(j, i)];
@@ -223,17 +226,6 @@ __device__ inline bool chol6_solve_packed(const double* Ap, const double* dd, co
         y[i] = v * il[i];
     }
     return true;
-}
-
-// 1/a to ~1 ulp without the IEEE division sequence: MUFU.RCP64H seed + two Newton steps (5 issue slots
-// instead of ~14 DFMA-equivalents measured for a correctly rounded division on B200).
-__device__ __forceinline__ double fast_rcp(double a) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double e = fma(-a, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-a, y, 1.0);
-    return fma(y, e, y);
 }
 
 // rotation_conversions.py:39-68 quaternion_to_matrix, including its two_s = 2/|q| scaling

@@ -118,13 +118,14 @@ __device__ inline void lm_set_eval_point(LmState& L, const double* x) {
     double a, bq, cq;  // R = I + a [w]x + bR [w]x^2 ; Jl = I + bq [w]x + cq [w]x^2
     const bool big = th2 > DBL_EPSILON;
     if (big) {
-        const double th = sqrt(th2);
+        const double ith = rsqrt(th2), th = th2 * ith;
         double sn, cs;
         sincos(th, &sn, &cs);
-        a = sn / th;
+        a = sn * ith;
         if (th2 > 1e-6) {
-            bq = (1.0 - cs) / th2;
-            cq = (th - sn) / (th2 * th);
+            const double ith2 = ith * ith;
+            bq = (1.0 - cs) * ith2;
+            cq = (th - sn) * ith2 * ith;
         } else {
             bq = 0.5 - th2 / 24.0;
             cq = 1.0 / 6.0 - th2 / 120.0;
@@ -168,7 +169,7 @@ __device__ inline bool lm_take_normal_eq(LmState& L, const double* fin, bool fir
     if (!finite) return false;
     if (first) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) L.scale[k] = 1.0 / (1.0 + sqrt(JtJ[sym_idx(k, k)]));
+        for (int k = 0; k < 6; ++k) L.scale[k] = fast_rcp(1.0 + sqrt(JtJ[sym_idx(k, k)]));
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -218,12 +219,12 @@ __device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool 
         sn = sqrt(sn);
         if (armed && sn <= ptol * (L.xnorm + ptol)) { L.term = TERM_CONVERGENCE; L.ctl = CTL_STOP; return; }
         if (armed && fabs(L.cost - cost_c) <= ftol * L.cost) { L.term = TERM_CONVERGENCE; L.ctl = CTL_STOP; return; }
-        const double rho = cost_c >= DBL_MAX ? -DBL_MAX : (L.cost - cost_c) / L.model_change;
+        const double rho = cost_c >= DBL_MAX ? -DBL_MAX : (L.cost - cost_c) * fast_rcp(L.model_change);
         if (rho > min_rel_dec) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) L.x[k] = L.xc[k];
             const double t = 2.0 * rho - 1.0;
-            L.radius = fmin(max_radius, L.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+            L.radius = fmin(max_radius, L.radius * fast_rcp(fmax(1.0 / 3.0, 1.0 - t * t * t)));
             L.dec = 2.0; L.reuse_diag = 0; L.step_ok = 1; L.any_success = 1;
             if (kind == CTL_EVAL_COST) { L.ctl = CTL_EVAL_JAC; return; }   // normal equations still missing
             if (!lm_take_normal_eq(L, fin, false)) { L.term = TERM_FAILURE; L.ctl = CTL_STOP; return; }
@@ -245,8 +246,9 @@ __device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool 
             for (int k = 0; k < 6; ++k) L.diag[k] = fmin(fmax(L.A[sym_idx(k, k)], min_diag), max_diag);
         }
         double dd[6], y[6];
+        const double inv_radius = fast_rcp(L.radius);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dd[k] = L.diag[k] / L.radius;
+        for (int k = 0; k < 6; ++k) dd[k] = L.diag[k] * inv_radius;
         bool valid = chol6_solve_packed(L.A, dd, L.gs, y);
         L.reuse_diag = 1;
         double mc = 0.0;
@@ -406,33 +408,49 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         s.vC[tid] = vc; s.vM[tid] = vm; s.u[tid] = uu;
     }
     __syncthreads();
-    if (tid == 0) {
+    // per-corner sums on 8 threads, then the scalar loss on one
+    if (tid < 8) {
+        const int j = tid;
+        s.wC[j] = s.vC[3 * j] + s.vC[3 * j + 1] + s.vC[3 * j + 2];
+        s.wM[j] = s.vM[3 * j] + s.vM[3 * j + 1] + s.vM[3 * j + 2];
+        s.wU[j] = sqrt(s.u[3 * j] * s.u[3 * j] + s.u[3 * j + 1] * s.u[3 * j + 1] + s.u[3 * j + 2] * s.u[3 * j + 2]);
+    }
+    if (tid == 32 % NT) {
         bool goodC = true, goodM = true;
         for (int k = 0; k < 24; ++k) { goodC = goodC && (s.vC[k] > 0.0); goodM = goodM && (s.vM[k] > 0.0); }
-        double prior = 0.0, cov_err = 0.0, lin = 0.0, sC[8], sM[8], un[8];
-        for (int j = 0; j < 8; ++j) {
-            sC[j] = s.vC[3 * j] + s.vC[3 * j + 1] + s.vC[3 * j + 2];
-            sM[j] = s.vM[3 * j] + s.vM[3 * j + 1] + s.vM[3 * j + 2];
-            un[j] = sqrt(s.u[3 * j] * s.u[3 * j] + s.u[3 * j + 1] * s.u[3 * j + 1] + s.u[3 * j + 2] * s.u[3 * j + 2]);
-            prior += sqrt(goodC ? sC[j] : 1.0);
-            cov_err += sqrt(goodM ? sM[j] : 1.0);
-            lin += un[j];
-        }
-        prior *= 0.125; cov_err *= 0.125; lin *= 0.125;
-        const double loss = log(prior) + 0.5 * (cov_err + lin) / prior;
-        if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], loss);
         if (!goodC) s.flag |= LC_ST_PRIOR_NOT_GOOD;
         if (!goodM) s.flag |= LC_ST_COV_NOT_GOOD;
-        if (a.lc_flags) a.lc_flags[b] = s.flag;
-        const double go = a.grad_scale * (a.grad_out.ptr ? ld<T>(a.grad_out, b * a.grad_out.stride[0]) : 1.0);
-        const double g_p = go * (1.0 / prior - 0.5 * (cov_err + lin) / (prior * prior));
-        const double g_c = go * 0.5 / prior;
-        for (int j = 0; j < 8; ++j) {
-            s.wC[j] = goodC ? g_p / (16.0 * sqrt(sC[j])) : 0.0;
-            s.wM[j] = goodM ? g_c / (16.0 * sqrt(sM[j])) : 0.0;
-            s.wU[j] = un[j] > 0.0 ? g_c * 0.125 / un[j] : 0.0;
-        }
     }
+    __syncthreads();
+    const bool goodC = !(s.flag & LC_ST_PRIOR_NOT_GOOD), goodM = !(s.flag & LC_ST_COV_NOT_GOOD);
+    double rsC = 0.0, rsM = 0.0, un = 0.0;
+    if (tid < 8) {
+        // 1/sqrt of the per-corner variances: sqrt(x) = x * rsqrt(x)
+        rsC = goodC ? rsqrt(s.wC[tid]) : 1.0;
+        rsM = goodM ? rsqrt(s.wM[tid]) : 1.0;
+        un = s.wU[tid];
+        s.T1[tid] = goodC ? s.wC[tid] * rsC : 1.0;        // sqrt terms of prior
+        s.T1[8 + tid] = goodM ? s.wM[tid] * rsM : 1.0;    // sqrt terms of cov_err
+    }
+    __syncthreads();
+    if (tid < 8) {
+        double prior = 0.0, cov_err = 0.0, lin = 0.0;
+        for (int j = 0; j < 8; ++j) { prior += s.T1[j]; cov_err += s.T1[8 + j]; lin += s.wU[j]; }
+        prior *= 0.125; cov_err *= 0.125; lin *= 0.125;
+        const double ip = fast_rcp(prior);
+        const double go = a.grad_scale * (a.grad_out.ptr ? ld<T>(a.grad_out, b * a.grad_out.stride[0]) : 1.0);
+        const double g_p = go * (ip - 0.5 * (cov_err + lin) * ip * ip);
+        const double g_c = go * 0.5 * ip;
+        if (tid == 0) {
+            if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], log(prior) + 0.5 * (cov_err + lin) * ip);
+            if (a.lc_flags) a.lc_flags[b] = s.flag;
+        }
+        s.T2[tid] = goodC ? g_p * 0.0625 * rsC : 0.0;
+        s.T2[8 + tid] = goodM ? g_c * 0.0625 * rsM : 0.0;
+        s.T2[16 + tid] = un > 0.0 ? g_c * 0.125 * fast_rcp(un) : 0.0;
+    }
+    __syncthreads();
+    if (tid < 8) { s.wC[tid] = s.T2[tid]; s.wM[tid] = s.T2[8 + tid]; s.wU[tid] = s.T2[16 + tid]; }
     if (a.cov.ptr)
         for (int e = tid; e < 36; e += NT) st<T>(a.cov, b * a.cov.stride[0] + (e / 6) * a.cov.stride[1] + (e % 6) * a.cov.stride[2], s.C[e]);
     if (a.update_cov.ptr)
