@@ -179,7 +179,7 @@ def main():
     from lc_b200.fused import solve_and_loss
     from lc_b200.cov_mixed import loss_fwd_bwd
     from lc_b200.pnp.cer_solver import lm_solve
-    from lc_b200.sharded import global_mean
+    from lc_b200.sharded import global_mean_from_sums
     from lc_b200 import _native as nat
 
     if not torch.cuda.is_available():
@@ -205,19 +205,25 @@ def main():
         return d["pts3d"].transpose(1, 2), d["pts2d"].transpose(1, 2), d["inv_std"].transpose(1, 2)
 
     outs = {}
+    # [sum of losses, count] accumulators the kernel adds into; a small ring so consecutive steps do not alias
+    sums = torch.zeros(8, 2, dtype=torch.float64, device=dev)
+    counter = [0]
 
     def step(d, out):
         p3, p2, s = views(d)
+        acc = None
+        if world > 1 and a.pipeline != "p2":
+            acc = sums[counter[0] % 8]
+            counter[0] += 1
+            acc.zero_()
         if a.pipeline == "p3":
-            r = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, out=out)
-            loss = r["loss"]
+            r = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, out=out, loss_sum=acc)
         elif a.pipeline == "p1":
-            r = loss_fwd_bwd(d["K"], d["pose"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go)
-            loss = r["loss"]
+            r = loss_fwd_bwd(d["K"], d["pose"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, loss_sum=acc)
         else:
             r = lm_solve(d["K"], p3, p2, s, d["start"], weight_mode=nat.W_INV_STD)
-            loss = r["radius"]
-        m = global_mean(loss) if world > 1 else None   # the path's only exchange: a 16-byte all-reduce
+        # the path's only exchange: one 16-byte all-reduce of [sum of losses, count] (losses.py:334,386 take the mean)
+        m = global_mean_from_sums(acc) if acc is not None else None
         return r, m
 
     def barrier():

@@ -110,6 +110,8 @@ typedef struct lc_args {
     int32_t* iters;     /* (B) LM iterations taken, or NULL */
     int32_t* lc_flags;  /* (B) LC_ST_* bits, or NULL */
     double* trace;      /* (B, max_iter+2, 4) [cost, radius, step_ok, gmax] per finalised iteration, or NULL */
+    double* loss_sum;   /* (2) += [sum_b loss_b, B] by atomicAdd (caller zeroes): the operand of the one scalar
+                           all-reduce a batch-sharded mean needs (losses.py:334,386), or NULL */
 } lc_args;
 
 int lc_b200_abi_version(void);

@@ -52,7 +52,8 @@ class lc_args(C.Structure):
                 + [(f, lc_view) for f in _VIEW_FIELDS]
                 + [("n_points", C.c_void_p)]
                 + [(f, lc_view) for f in _OUT_VIEW_FIELDS]
-                + [("invalid", C.c_void_p), ("iters", C.c_void_p), ("lc_flags", C.c_void_p), ("trace", C.c_void_p)])
+                + [("invalid", C.c_void_p), ("iters", C.c_void_p), ("lc_flags", C.c_void_p), ("trace", C.c_void_p),
+                   ("loss_sum", C.c_void_p)])
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -178,10 +179,10 @@ def make_args(B: int, N: int, dtype: torch.dtype, **kw) -> lc_args:
             if v is not None and v.dtype != torch.int32:
                 raise TypeError(f"{k} must be int32")
             setattr(a, k, None if v is None else v.data_ptr())
-        elif k == "trace":
+        elif k in ("trace", "loss_sum"):
             if v is not None and v.dtype != torch.float64:
-                raise TypeError("trace must be float64")
-            a.trace = None if v is None else v.data_ptr()
+                raise TypeError(f"{k} must be float64")
+            setattr(a, k, None if v is None else v.data_ptr())
         else:
             setattr(a, k, v)
     return a

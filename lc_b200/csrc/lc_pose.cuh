@@ -442,8 +442,10 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         const double g_p = go * (ip - 0.5 * (cov_err + lin) * ip * ip);
         const double g_c = go * 0.5 * ip;
         if (tid == 0) {
-            if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], log(prior) + 0.5 * (cov_err + lin) * ip);
+            const double loss = log(prior) + 0.5 * (cov_err + lin) * ip;
+            if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], loss);
             if (a.lc_flags) a.lc_flags[b] = s.flag;
+            if (a.loss_sum) { atomicAdd(a.loss_sum, loss); atomicAdd(a.loss_sum + 1, 1.0); }
         }
         s.T2[tid] = goodC ? g_p * 0.0625 * rsC : 0.0;
         s.T2[8 + tid] = goodM ? g_c * 0.0625 * rsM : 0.0;

@@ -17,7 +17,8 @@ from . import _native as nat
 def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std: Tensor, valid: Optional[Tensor],
                    bbox_3d: Tensor, *, max_iter_count=50, function_tolerance=1e-6, max_err_len=32.0, rel_thresh=3.0,
                    w_e_thresh=4.0, need=(True, False, True), grad_out: Optional[Tensor] = None, grad_scale=1.0,
-                   tol_needs_success=True, out: Optional[dict] = None, force_streaming=False):
+                   tol_needs_success=True, out: Optional[dict] = None, force_streaming=False,
+                   loss_sum: Optional[Tensor] = None):
     """Returns dict(states, radius, invalid, iters, loss, g_pts3d, g_pts2d, g_inv_std, flags).
 
     ``out`` may carry preallocated output tensors from a previous call (same shapes) to avoid allocation.
@@ -43,6 +44,6 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
                          state=res["states"], radius=res["radius"], invalid=res["invalid"], iters=res["iters"],
                          lc_flags=res["flags"], flags=flags, weight_mode=nat.W_INV_STD, max_iter=int(max_iter_count),
                          function_tolerance=ftol, max_err_len=float(max_err_len), rel_thresh=float(rel_thresh),
-                         w_e_thresh=float(w_e_thresh), grad_scale=float(grad_scale))
+                         w_e_thresh=float(w_e_thresh), grad_scale=float(grad_scale), loss_sum=loss_sum)
     res["launches"] = nat.call("lc_b200_solve_loss", args, dev)
     return res

@@ -32,13 +32,13 @@ def test_struct_layout_matches_header(tmp_path):
     c = tmp_path / "sz.c"
     c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu",'
                  'sizeof(lc_args),offsetof(lc_args,K),offsetof(lc_args,n_points),offsetof(lc_args,loss),'
-                 'offsetof(lc_args,invalid),offsetof(lc_args,trace));return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
+                 'offsetof(lc_args,invalid),offsetof(lc_args,loss_sum));return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
     exe = tmp_path / "sz"
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([gcc, "-o", str(exe), str(c)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     A = nat.lc_args
-    assert got == [ctypes.sizeof(A), A.K.offset, A.n_points.offset, A.loss.offset, A.invalid.offset, A.trace.offset]
+    assert got == [ctypes.sizeof(A), A.K.offset, A.n_points.offset, A.loss.offset, A.invalid.offset, A.loss_sum.offset]
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

@@ -41,3 +41,17 @@ def test_fused_equals_solver_then_loss():
     assert torch.equal(f["loss"], l["loss"])
     for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
         assert torch.equal(f[k], l[k])
+
+
+def test_loss_sum_accumulator_and_sharded_mean():
+    """lc_args.loss_sum: the kernel adds [sum of losses, pose count]; sharded_mean_loss scales gradients by 1/B_global."""
+    from lc_b200.cov_mixed import loss_fwd_bwd
+    from lc_b200.sharded import sharded_mean_loss
+    c = make_correspondences(12, 300, 9).to(torch.float32).to(device="cuda")
+    base = loss_fwd_bwd(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
+    mean, out = sharded_mean_loss(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d, global_batch=24)
+    assert torch.allclose(mean.double(), base["loss"].double().mean(), rtol=1e-6)
+    assert rel_err(out["g_pts3d"].cpu().numpy(), (base["g_pts3d"] / 24).cpu().numpy()) <= 1e-5
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    loss_fwd_bwd(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d, loss_sum=acc, force_streaming=True)
+    assert acc[1].item() == 12 and abs(acc[0].item() - base["loss"].double().sum().item()) < 1e-4
