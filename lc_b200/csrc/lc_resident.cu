@@ -13,9 +13,9 @@
 //             accumulation, reverse pass) are fp32 per point with per-thread partial sums of <= N/NT terms
 //             that are reduced across the CTA in fp64; the 6x6 algebra is fp64 (lc_pose.cuh).
 //
-// Loss-only launches (MODE == 2) skip the raw staging: pass 1 streams X/x from HBM straight into P/ec
-// (20 B/point of shared memory) and the weights are re-read from L2, so two CTAs fit per SM and one CTA's
-// load / 6x6 sections overlap the other's point passes.
+// Staging uses cp.async (LDGSTS): every element of the pose is in flight at once while the pose constants are set up.
+// Loss-only launches (MODE == 2) stage only X and x (20 B/point) and re-read the weights from L2, so two CTAs fit
+// per SM and one CTA's load / 6x6 sections overlap the other's point passes.
 //
 // Restrictions (anything else takes the streaming kernel): fp32 tensors, diagonal weights, 64 < N <= limit.
 #include <cstdio>
@@ -53,6 +53,16 @@ __device__ __forceinline__ float nan_to_num_f(float x) {
     if (isnan(x)) return 0.f;
     if (isinf(x)) return x > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
     return x;
+}
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register staging, every copy of a pose is in flight at once
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
@@ -113,6 +123,25 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_ker
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
 
+    // ---- stage the correspondences: one asynchronous copy per element, all in flight while the pose constants
+    //      are set up (coalesced for the planar layout of the dense call site; any strides accepted) ----
+    {
+        const float* p3 = static_cast<const float*>(a.pts3d.ptr) + b * a.pts3d.stride[0];
+        const float* p2 = static_cast<const float*>(a.pts2d.ptr) + b * a.pts2d.stride[0];
+        const float* pw = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
+        const int64_t s3n = a.pts3d.stride[1], s3c = a.pts3d.stride[2], s2n = a.pts2d.stride[1], s2c = a.pts2d.stride[2];
+        const int64_t swn = a.weights.stride[1], swc = a.weights.stride[2];
+        for (int i = tid; i < npad; i += NT) {
+            if (i < n) {
+                cp_async4(l.A0 + i, p3 + i * s3n); cp_async4(l.A1 + i, p3 + i * s3n + s3c); cp_async4(l.A2 + i, p3 + i * s3n + 2 * s3c);
+                cp_async4(l.B0 + i, p2 + i * s2n); cp_async4(l.B1 + i, p2 + i * s2n + s2c);
+                if (RAW) { cp_async4(l.S0 + i, pw + i * swn); cp_async4(l.S1 + i, pw + i * swn + swc); }
+            } else {
+                l.A0[i] = 0.f; l.A1[i] = 0.f; l.A2[i] = 0.f; l.B0[i] = 0.f; l.B1[i] = 0.f;
+                if (RAW) { l.S0[i] = 0.f; l.S1[i] = 0.f; }
+            }
+        }
+    }
     // ---- pose constants ----
     if (tid < 9) {
         float v = ldf(a.K, b * a.K.stride[0] + (tid / 3) * a.K.stride[1] + (tid % 3) * a.K.stride[2]);
@@ -125,28 +154,18 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_ker
         for (int k = tid; k < 24; k += NT)
             s.bbox[k] = ldf(a.bbox, b * a.bbox.stride[0] + (k / 3) * a.bbox.stride[1] + (k % 3) * a.bbox.stride[2]);
     }
-
-    // ---- stage the raw correspondences once (coalesced for the planar layout; any strides accepted) ----
-    if (RAW) {
-        const int64_t o3b = b * a.pts3d.stride[0], o2b = b * a.pts2d.stride[0], owb = b * a.weights.stride[0];
-        for (int i = tid; i < npad; i += NT) {
-            float X0 = 0.f, X1 = 0.f, X2 = 0.f, x0 = 0.f, x1 = 0.f, w0 = 0.f, w1 = 0.f;
-            if (i < n) {
-                const int64_t o3 = o3b + i * a.pts3d.stride[1];
-                X0 = ldf(a.pts3d, o3); X1 = ldf(a.pts3d, o3 + a.pts3d.stride[2]); X2 = ldf(a.pts3d, o3 + 2 * a.pts3d.stride[2]);
-                const int64_t o2 = o2b + i * a.pts2d.stride[1];
-                x0 = ldf(a.pts2d, o2); x1 = ldf(a.pts2d, o2 + a.pts2d.stride[2]);
-                const int64_t ow = owb + i * a.weights.stride[1];
-                w0 = ldf(a.weights, ow); w1 = ldf(a.weights, ow + a.weights.stride[2]);
-                if (sanitize) {
-                    X0 = nan_to_num_f(X0); X1 = nan_to_num_f(X1); X2 = nan_to_num_f(X2);
-                    x0 = nan_to_num_f(x0); x1 = nan_to_num_f(x1); w0 = nan_to_num_f(w0); w1 = nan_to_num_f(w1);
-                }
-                // cer_solver.py:37-38: L = diag(sqrt(icov)).  For LC_W_INV_STD the reference computes
-                // sqrt(fl(s*s)) in fp32, which is exactly |s| (barring overflow/underflow of s*s): kept raw, |.| at use.
-                if (a.weight_mode == LC_W_ICOV_DIAG) { w0 = sqrtf(w0); w1 = sqrtf(w1); }
+    cp_async_commit_wait_all();
+    if (RAW && (sanitize || a.weight_mode == LC_W_ICOV_DIAG)) {
+        // solver prologue on the thread's own elements: nan_to_num (cer_solver.py:27-29), L = diag(sqrt(icov)) (:37-38).
+        // For LC_W_INV_STD the reference computes sqrt(fl(s*s)) in fp32, which is exactly |s| (barring overflow /
+        // underflow of s*s): the weights stay raw and |.| is taken at use.
+        for (int i = tid; i < n; i += NT) {
+            if (sanitize) {
+                l.A0[i] = nan_to_num_f(l.A0[i]); l.A1[i] = nan_to_num_f(l.A1[i]); l.A2[i] = nan_to_num_f(l.A2[i]);
+                l.B0[i] = nan_to_num_f(l.B0[i]); l.B1[i] = nan_to_num_f(l.B1[i]);
+                l.S0[i] = nan_to_num_f(l.S0[i]); l.S1[i] = nan_to_num_f(l.S1[i]);
             }
-            l.A0[i] = X0; l.A1[i] = X1; l.A2[i] = X2; l.B0[i] = x0; l.B1[i] = x1; l.S0[i] = w0; l.S1[i] = w1;
+            if (a.weight_mode == LC_W_ICOV_DIAG) { l.S0[i] = sqrtf(l.S0[i]); l.S1[i] = sqrtf(l.S1[i]); }
         }
     }
     __syncthreads();
@@ -186,7 +205,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_ker
     if (tid == 0) lc_pose_setup(s, true);
     __syncthreads();
 
-    const int64_t o3b = b * a.pts3d.stride[0], o2b = b * a.pts2d.stride[0], owb = b * a.weights.stride[0];
+    const int64_t owb = b * a.weights.stride[0];
     const int64_t ovb = a.valid.ptr ? b * a.valid.stride[0] : 0;
     // pass 1 (fp64): P = R X + t, project_apply + clamp_error once per point; P, ec kept as fp32 in place
     {
@@ -194,15 +213,7 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_ker
         const double lim = Lmax - 1e-6, lim2 = lim > 0.0 ? lim * lim : -1.0;   // |e|+1e-6 > Lmax  <=>  |e|^2 > lim2
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
         for (int i = tid; i < n; i += NT) {
-            double X0, X1, X2, x0, x1;
-            if (RAW) {
-                X0 = l.A0[i]; X1 = l.A1[i]; X2 = l.A2[i]; x0 = l.B0[i]; x1 = l.B1[i];
-            } else {
-                const int64_t o3 = o3b + i * a.pts3d.stride[1];
-                X0 = ldf(a.pts3d, o3); X1 = ldf(a.pts3d, o3 + a.pts3d.stride[2]); X2 = ldf(a.pts3d, o3 + 2 * a.pts3d.stride[2]);
-                const int64_t o2 = o2b + i * a.pts2d.stride[1];
-                x0 = ldf(a.pts2d, o2); x1 = ldf(a.pts2d, o2 + a.pts2d.stride[2]);
-            }
+            const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i], x0 = l.B0[i], x1 = l.B1[i];
             const double q0 = fma(s.R[0], X0, fma(s.R[1], X1, s.R[2] * X2));
             const double q1 = fma(s.R[3], X0, fma(s.R[4], X1, s.R[5] * X2));
             const double q2 = fma(s.R[6], X0, fma(s.R[7], X1, s.R[8] * X2));
