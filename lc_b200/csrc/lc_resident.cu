@@ -1,9 +1,10 @@
 // lc_b200 — shared-memory resident sm_100a kernel for the LC hot path (the headline path).
 //
 // One CTA per pose.  The pose's correspondences are read from HBM exactly once, converted to a planar
-// fp32 layout in shared memory (28 B/point: X[3], x[2], w[2]), and every later pass runs out of shared
-// memory; the only other HBM traffic is the gradient write-back.  DRAM bytes = the algorithmic
-// 48*N + O(1) per pose.
+// fp32 layout in shared memory (20 B/point: X[3], x[2]); the weights (8 B/point) are re-read from L2 by the
+// passes that need them, which keeps the footprint at N = 4096 small enough for TWO CTAs per SM, so one
+// CTA's serial sections (trust-region step, 6x6 algebra) and loads overlap the other's point passes.  The only
+// other HBM traffic is the gradient write-back.  DRAM bytes = the algorithmic 48*N + O(1) per pose.
 //
 //   LM phase  (MODE & 1): fp64.  Each trust-region iteration is one fused pass (cost + J'^T J' + J'^T r in
 //             the left basis, 28 accumulators/thread) + one multi-value CTA reduction + a single-thread
@@ -19,6 +20,7 @@
 //
 // Restrictions (anything else takes the streaming kernel): fp32 tensors, diagonal weights, 64 < N <= limit.
 #include <cstdio>
+#include <cstdlib>
 
 #include "lc_pose.cuh"
 
@@ -68,7 +70,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 // One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
 // staged fp32 arrays: cost, and when JAC also J'^T J' and J'^T r in the left basis.
 template <int NT, bool JAC>
-__device__ __forceinline__ void lm_eval_pass_res(PoseShared& s, const ResLayout& l, int n) {
+__device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
     const LmState& L = s.lm;
     double acc[28];
 #pragma unroll
@@ -76,11 +78,26 @@ __device__ __forceinline__ void lm_eval_pass_res(PoseShared& s, const ResLayout&
     const double k00 = s.K[0], k01 = s.K[1], k10 = s.K[3], k11 = s.K[4], cx = s.K[2], cy = s.K[5];
     const double R0 = L.Rm[0], R1 = L.Rm[1], R2 = L.Rm[2], R3 = L.Rm[3], R4 = L.Rm[4], R5 = L.Rm[5], R6 = L.Rm[6], R7 = L.Rm[7], R8 = L.Rm[8];
     const double t0 = L.te[0], t1 = L.te[1], t2 = L.te[2];
-#pragma unroll 1
-    for (int i = threadIdx.x; i < n; i += NT) {
+    // the sqrt-information weights are re-read from L2 every pass (8 B/point) instead of living in shared memory:
+    // that is what lets two CTAs share an SM at N = 4096.  The next point's weights are fetched before the
+    // current point is processed.
+    const float* pw = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
+    const int64_t swn = a.weights.stride[1], swc = a.weights.stride[2];
+    const bool icov = a.weight_mode == LC_W_ICOV_DIAG;
+    int i = threadIdx.x;
+    float w0 = 0.f, w1 = 0.f;
+    if (i < n) { w0 = pw[i * swn]; w1 = pw[i * swn + swc]; }
+    for (; i < n; i += NT) {
+        float wa = w0, wb = w1;
+        const int inext = i + NT;
+        if (inext < n) { w0 = pw[inext * swn]; w1 = pw[inext * swn + swc]; }
+        if (sanitize) { wa = nan_to_num_f(wa); wb = nan_to_num_f(wb); }
+        // cer_solver.py:37-38: L = diag(sqrt(icov)) in fp32.  For LC_W_INV_STD the reference's sqrt(fl(s*s)) is exactly
+        // |s| (barring overflow / underflow of s*s).
+        if (icov) { wa = sqrtf(wa); wb = sqrtf(wb); }
+        const double la = fabsf(wa), lc_ = fabsf(wb);
         const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i];
         const double px = l.B0[i], py = l.B1[i];
-        const double la = fabsf(l.S0[i]), lc_ = fabsf(l.S1[i]);
         const double q0 = fma(R0, X0, fma(R1, X1, R2 * X2));
         const double q1 = fma(R3, X0, fma(R4, X1, R5 * X2));
         const double q2 = fma(R6, X0, fma(R7, X1, R8 * X2));
@@ -113,9 +130,9 @@ __device__ __forceinline__ void lm_eval_pass_res(PoseShared& s, const ResLayout&
 }
 
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_kernel(const lc_args a, int npad) {
+__global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int npad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool RAW = (MODE & MODE_LM) != 0;
+    constexpr bool RAW = false;   // weights are never staged: they are streamed from L2 (see lm_eval_pass_res)
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
     const ResLayout l = res_layout(smem_raw, npad, RAW);
     const int b = blockIdx.x;
@@ -155,17 +172,11 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_ker
             s.bbox[k] = ldf(a.bbox, b * a.bbox.stride[0] + (k / 3) * a.bbox.stride[1] + (k % 3) * a.bbox.stride[2]);
     }
     cp_async_commit_wait_all();
-    if (RAW && (sanitize || a.weight_mode == LC_W_ICOV_DIAG)) {
-        // solver prologue on the thread's own elements: nan_to_num (cer_solver.py:27-29), L = diag(sqrt(icov)) (:37-38).
-        // For LC_W_INV_STD the reference computes sqrt(fl(s*s)) in fp32, which is exactly |s| (barring overflow /
-        // underflow of s*s): the weights stay raw and |.| is taken at use.
+    if (sanitize) {
+        // solver prologue on the thread's own elements: nan_to_num (cer_solver.py:27-29)
         for (int i = tid; i < n; i += NT) {
-            if (sanitize) {
-                l.A0[i] = nan_to_num_f(l.A0[i]); l.A1[i] = nan_to_num_f(l.A1[i]); l.A2[i] = nan_to_num_f(l.A2[i]);
-                l.B0[i] = nan_to_num_f(l.B0[i]); l.B1[i] = nan_to_num_f(l.B1[i]);
-                l.S0[i] = nan_to_num_f(l.S0[i]); l.S1[i] = nan_to_num_f(l.S1[i]);
-            }
-            if (a.weight_mode == LC_W_ICOV_DIAG) { l.S0[i] = sqrtf(l.S0[i]); l.S1[i] = sqrtf(l.S1[i]); }
+            l.A0[i] = nan_to_num_f(l.A0[i]); l.A1[i] = nan_to_num_f(l.A1[i]); l.A2[i] = nan_to_num_f(l.A2[i]);
+            l.B0[i] = nan_to_num_f(l.B0[i]); l.B1[i] = nan_to_num_f(l.B1[i]);
         }
     }
     __syncthreads();
@@ -186,8 +197,8 @@ __global__ void __launch_bounds__(NT, (MODE == MODE_LC) ? 2 : 1) lc_resident_ker
             bool first = true;
             for (;;) {
                 const int kind = L.ctl;
-                if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(s, l, n);
-                else lm_eval_pass_res<NT, true>(s, l, n);
+                if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(a, s, l, b, n, sanitize);
+                else lm_eval_pass_res<NT, true>(a, s, l, b, n, sanitize);
                 if (tid == 0)
                     lm_advance(L, s.fin, kind, first, a.max_iter, a.function_tolerance, (a.flags & LC_FLAG_TOL_NEEDS_SUCCESS) != 0, trace);
                 first = false;
@@ -411,19 +422,15 @@ static int max_optin_smem() {
 bool resident_supported(const lc_args& a, int mode) {
     if (a.dtype != LC_F32 || a.N < kResidentMinN) return false;
     if ((mode & MODE_LM) && a.weight_mode != LC_W_ICOV_DIAG && a.weight_mode != LC_W_INV_STD) return false;
-    const size_t need = resident_smem_bytes(a.N, (mode & MODE_LM) != 0);
+    const size_t need = resident_smem_bytes(a.N, false);
     return need <= static_cast<size_t>(max_optin_smem());
 }
 
-static int resident_threads_for(int n) {
-    if (n <= 512) return 128;
-    if (n <= 2048) return 256;
-    return 512;
-}
+static int resident_threads_for(int n) { return n <= 512 ? 128 : 256; }
 
 template <int NT, int MODE>
 static int launch_res_t(const lc_args& a, cudaStream_t st) {
-    const size_t smem = resident_smem_bytes(a.N, (MODE & MODE_LM) != 0);
+    const size_t smem = resident_smem_bytes(a.N, false);
     static size_t configured = 0;   // per instantiation
     if (smem > configured) {
         const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_optin_smem()));
@@ -436,14 +443,10 @@ static int launch_res_t(const lc_args& a, cudaStream_t st) {
 
 template <int MODE>
 static int launch_res_m(const lc_args& a, cudaStream_t st) {
-    const int nt = resident_threads_for(a.N);
-    if (nt == 128) return launch_res_t<128, MODE>(a, st);
-    if constexpr (MODE == MODE_LC) {
-        return launch_res_t<256, MODE>(a, st);   // loss-only: 2 CTAs of 256 threads per SM (see file header)
-    } else {
-        if (nt == 256) return launch_res_t<256, MODE>(a, st);
-        return launch_res_t<512, MODE>(a, st);
-    }
+    // 256 threads x 2 CTAs per SM (20 B/point of shared memory): one CTA's 6x6 / trust-region sections and loads
+    // overlap the other CTA's point passes
+    if (resident_threads_for(a.N) == 128) return launch_res_t<128, MODE>(a, st);
+    return launch_res_t<256, MODE>(a, st);
 }
 
 int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st) {
