@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Scaling sweep of the LC operators (BASELINE.json configs[4]): B in {1..65536} x N in {8, 1024, 4096}, pipelines
+p1 (loss fwd+bwd), p2 (LM solve), p3 (fused).  One GPU per process; run under torchrun for several GPUs (each rank
+sweeps its own shard of B and rank 0 reports the max-over-ranks time).
+
+    python tools/sweep.py [--out profiles/sweep_r1.md] [--max-bytes 8e9]
+
+Per point: poses/s, algorithmic GB/s, fraction of the measured HBM peak.  CUDA events around `reps` back-to-back
+launches after 3 warm-ups; inputs rotate over enough distinct batches to exceed L2 when they are small.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from lc_b200 import _native as nat  # noqa: E402
+from lc_b200.cov_mixed import loss_fwd_bwd  # noqa: E402
+from lc_b200.fused import solve_and_loss  # noqa: E402
+from lc_b200.pnp.cer_solver import lm_solve  # noqa: E402
+from lc_b200.synth import make_correspondences  # noqa: E402
+
+
+def bytes_per_pose(p, n):
+    return 28 * n + 104 if p == "p2" else 48 * n + (228 if p == "p3" else 164)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--max-bytes", type=float, default=6e9)
+    ap.add_argument("--points", default="8,1024,4096")
+    ap.add_argument("--bmax", type=int, default=65536)
+    a = ap.parse_args()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    peak = 6436.4
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk))["hbm_gbs"])
+    rows = []
+    for n in [int(x) for x in a.points.split(",")]:
+        B = 1
+        while B <= a.bmax:
+            in_bytes = B * n * 28
+            if in_bytes * 2 > a.max_bytes:
+                break
+            nrot = max(1, min(4, int(3e8 // max(in_bytes, 1)) + 1))   # rotate inputs to defeat L2 when they are small
+            sets = []
+            base = make_correspondences(min(B, 256), n, 7).to(torch.float32)
+            rep = (B + base.pts3d.shape[0] - 1) // base.pts3d.shape[0]
+            for r in range(nrot):
+                t = lambda x: x.repeat((rep,) + (1,) * (x.dim() - 1))[:B].roll(r, 0).contiguous().to(dev)
+                sets.append(dict(K=t(base.K), pose=t(base.pose), start=t(base.start), bbox=t(base.bbox_3d),
+                                 p3=t(base.pts3d.transpose(1, 2)).transpose(1, 2), p2=t(base.pts2d.transpose(1, 2)).transpose(1, 2),
+                                 s=t(base.inv_std.transpose(1, 2)).transpose(1, 2)))
+            go = torch.full((B,), 1.0 / B, device=dev)
+            for pipe in ("p1", "p2", "p3"):
+                def step(d):
+                    if pipe == "p1":
+                        loss_fwd_bwd(d["K"], d["pose"], d["p3"], d["p2"], d["s"], None, d["bbox"], need=(True, False, True), grad_out=go)
+                    elif pipe == "p2":
+                        lm_solve(d["K"], d["p3"], d["p2"], d["s"], d["start"], weight_mode=nat.W_INV_STD)
+                    else:
+                        solve_and_loss(d["K"], d["start"], d["p3"], d["p2"], d["s"], None, d["bbox"], need=(True, False, True), grad_out=go)
+                for i in range(3):
+                    step(sets[i % nrot])
+                reps = 20 if B * n < 2e7 else 8
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(reps):
+                    step(sets[i % nrot])
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                gbs = B * bytes_per_pose(pipe, n) / (ms * 1e-3) / 1e9
+                rows.append((n, B, pipe, ms * 1e3, B / (ms * 1e-3), gbs, gbs / peak))
+                print(f"N={n:5d} B={B:6d} {pipe}: {ms * 1e3:9.1f} us  {B / (ms * 1e-3):12.0f} poses/s  {gbs:8.1f} GB/s  {100 * gbs / peak:5.1f}% of HBM peak", flush=True)
+            del sets
+            torch.cuda.empty_cache()
+            B *= 4
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write("# LC operator sweep (1 x B200; CUDA events; launch overhead included)\n\n")
+            f.write(f"HBM peak used for the last column: {peak} GB/s (MEASURED_PEAKS.json).  p1 = loss fwd+bwd, p2 = LM solve, p3 = fused.\n\n")
+            f.write("| N | B | pipeline | us/launch | poses/s | algorithmic GB/s | % of HBM peak |\n|---|---|---|---|---|---|---|\n")
+            for r in rows:
+                f.write(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]:.1f} | {r[4]:.0f} | {r[5]:.1f} | {100 * r[6]:.1f} |\n")
+
+
+if __name__ == "__main__":
+    main()
