@@ -33,6 +33,7 @@ struct PoseShared {
     double wC[8], wM[8], wU[8];
     double cHL[kSym], cGL[kSym], bL[6];  // reverse-pass coefficients, left basis, packed (off-diagonals doubled)
     int flag, pad;
+    unsigned long long tma_bar;  // mbarrier of the TMA staging (lc_resident.cu)
     LmState lm;
 };
 

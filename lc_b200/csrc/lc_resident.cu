@@ -67,6 +67,29 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one instruction per contiguous slab ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
+
 // One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
 // staged fp32 arrays: cost, and when JAC also J'^T J' and J'^T r in the left basis.
 template <int NT, bool JAC>
@@ -130,7 +153,7 @@ __device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s
 }
 
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int npad) {
+__global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool RAW = false;   // weights are never staged: they are streamed from L2 (see lm_eval_pass_res)
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
@@ -140,22 +163,34 @@ __global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
 
-    // ---- stage the correspondences: one asynchronous copy per element, all in flight while the pose constants
-    //      are set up (coalesced for the planar layout of the dense call site; any strides accepted) ----
+    // ---- stage the correspondences.  Planar, 16-byte aligned arrays (what the dense call site produces, tma_mask
+    //      bit 0 = pts3d, bit 1 = pts2d) go through the TMA: one 1-D bulk copy per component slab, issued by one
+    //      thread, completing on an mbarrier.  Anything else: one 4-byte cp.async per element (any strides).  Either
+    //      way every byte of the pose is in flight while the pose constants are set up. ----
     {
         const float* p3 = static_cast<const float*>(a.pts3d.ptr) + b * a.pts3d.stride[0];
         const float* p2 = static_cast<const float*>(a.pts2d.ptr) + b * a.pts2d.stride[0];
-        const float* pw = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
         const int64_t s3n = a.pts3d.stride[1], s3c = a.pts3d.stride[2], s2n = a.pts2d.stride[1], s2c = a.pts2d.stride[2];
-        const int64_t swn = a.weights.stride[1], swc = a.weights.stride[2];
-        for (int i = tid; i < npad; i += NT) {
-            if (i < n) {
-                cp_async4(l.A0 + i, p3 + i * s3n); cp_async4(l.A1 + i, p3 + i * s3n + s3c); cp_async4(l.A2 + i, p3 + i * s3n + 2 * s3c);
-                cp_async4(l.B0 + i, p2 + i * s2n); cp_async4(l.B1 + i, p2 + i * s2n + s2c);
-                if (RAW) { cp_async4(l.S0 + i, pw + i * swn); cp_async4(l.S1 + i, pw + i * swn + swc); }
-            } else {
-                l.A0[i] = 0.f; l.A1[i] = 0.f; l.A2[i] = 0.f; l.B0[i] = 0.f; l.B1[i] = 0.f;
-                if (RAW) { l.S0[i] = 0.f; l.S1[i] = 0.f; }
+        const bool tma3 = (tma_mask & 1) != 0, tma2 = (tma_mask & 2) != 0;
+        if (tma_mask) {
+            if (tid == 0) mbar_init(&s.tma_bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned slab = static_cast<unsigned>(a.N) * 4u;
+                mbar_expect_tx(&s.tma_bar, slab * ((tma3 ? 3u : 0u) + (tma2 ? 2u : 0u)));
+                if (tma3) { tma_load_1d(l.A0, p3, slab, &s.tma_bar); tma_load_1d(l.A1, p3 + s3c, slab, &s.tma_bar); tma_load_1d(l.A2, p3 + 2 * s3c, slab, &s.tma_bar); }
+                if (tma2) { tma_load_1d(l.B0, p2, slab, &s.tma_bar); tma_load_1d(l.B1, p2 + s2c, slab, &s.tma_bar); }
+            }
+        }
+        if (!(tma3 && tma2)) {
+            for (int i = tid; i < npad; i += NT) {
+                if (i < n) {
+                    if (!tma3) { cp_async4(l.A0 + i, p3 + i * s3n); cp_async4(l.A1 + i, p3 + i * s3n + s3c); cp_async4(l.A2 + i, p3 + i * s3n + 2 * s3c); }
+                    if (!tma2) { cp_async4(l.B0 + i, p2 + i * s2n); cp_async4(l.B1 + i, p2 + i * s2n + s2c); }
+                } else {
+                    if (!tma3) { l.A0[i] = 0.f; l.A1[i] = 0.f; l.A2[i] = 0.f; }
+                    if (!tma2) { l.B0[i] = 0.f; l.B1[i] = 0.f; }
+                }
             }
         }
     }
@@ -172,6 +207,7 @@ __global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int
             s.bbox[k] = ldf(a.bbox, b * a.bbox.stride[0] + (k / 3) * a.bbox.stride[1] + (k % 3) * a.bbox.stride[2]);
     }
     cp_async_commit_wait_all();
+    if (tma_mask) mbar_wait(&s.tma_bar, 0);
     if (sanitize) {
         // solver prologue on the thread's own elements: nan_to_num (cer_solver.py:27-29)
         for (int i = tid; i < n; i += NT) {
@@ -426,7 +462,21 @@ bool resident_supported(const lc_args& a, int mode) {
     return need <= static_cast<size_t>(max_optin_smem());
 }
 
-static int resident_threads_for(int n) { return n <= 512 ? 128 : 256; }
+static int resident_threads_for(int n) {
+    if (const char* e = getenv("LC_B200_RES_NT")) return atoi(e);   // tuning knob for benchmarks
+    return n <= 512 ? 128 : 256;
+}
+
+// A (B,N,C) fp32 view can be staged by 1-D TMA bulk copies when every component slab is contiguous (point stride 1)
+// and 16-byte aligned for every pose: base pointer, batch stride, component stride and N all multiples of 16 bytes.
+static bool tma_ok(const lc_view& v, int n) {
+    return v.stride[1] == 1 && (n % 4) == 0 && (reinterpret_cast<uintptr_t>(v.ptr) % 16) == 0 && (v.stride[0] % 4) == 0 &&
+           (v.stride[2] % 4) == 0;
+}
+static int tma_mask_for(const lc_args& a) {
+    if (getenv("LC_B200_NO_TMA")) return 0;
+    return (tma_ok(a.pts3d, a.N) ? 1 : 0) | (tma_ok(a.pts2d, a.N) ? 2 : 0);
+}
 
 template <int NT, int MODE>
 static int launch_res_t(const lc_args& a, cudaStream_t st) {
@@ -437,7 +487,7 @@ static int launch_res_t(const lc_args& a, cudaStream_t st) {
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = static_cast<size_t>(max_optin_smem());
     }
-    lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(a.N));
+    lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(a.N), tma_mask_for(a));
     return static_cast<int>(cudaGetLastError());
 }
 
