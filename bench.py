@@ -88,25 +88,77 @@ def run_cpu_port(pipeline: str, n_pts: int, sample: int, steps: int, warmup: int
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled every ~5 ms through NVML (nvidia_ml_py) during the timed region;
+    falls back to `nvidia-smi -lms 20` if NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.lines, self.proc = gpu_index, [], None
+        self.idx, self.lines, self.proc, self.nvml, self.samples, self.stop_flag = gpu_index, [], None, None, [], False
+
+    def _nvml_loop(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.idx)
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    self.idx = int(vis.split(",")[self.idx])
+                except Exception:
+                    pass
+            self.thr = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.thr.start()
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=2)
+            n = self.nvml
+            h = n.nvmlDeviceGetHandleByIndex(self.idx)
+            sm = sorted(x[0] for x in self.samples)
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, v in names.items() if bits & v)
+            try:
+                mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.thr.join(timeout=2)
         sm, mx, reasons = [], [], set()
@@ -123,7 +175,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_gbs():
@@ -316,11 +368,11 @@ def main():
     bytes_per_launch = B * algorithmic_bytes_per_pose(a.pipeline, N)
     launch_s = ms * 1e-3 / a.steps
     achieved = bytes_per_launch / launch_s / 1e9
-    kernel = {"p3": "lc_pose_kernel<float,256,LM|LC>", "p1": "lc_pose_kernel<float,256,LC>", "p2": "lc_pose_kernel<float,256,LM>"}[a.pipeline]
+    kernel = {"p3": "lc::lc_resident_kernel<256, LM|LC>", "p1": "lc::lc_resident_kernel<256, LC>", "p2": "lc::lc_resident_kernel<256, LM>"}[a.pipeline]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(a.pipeline), "kernel": kernel, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "launch_us": launch_s * 1e6,
-                "note": "the kernel is FP64-pipe bound, not HBM bound (DESIGN.md §Roofline); frac is against the HBM copy peak as BASELINE.json asks"}
+                "note": "arithmetic/latency bound, not HBM bound (DESIGN.md 4.3): ~1.5k instructions per point incl. an fp64 LM; frac is against the measured HBM copy peak as BASELINE.json asks"}
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
