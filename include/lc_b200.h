@@ -56,7 +56,7 @@ enum {
 enum {
     LC_FLAG_NAN_TO_NUM = 1,        /* solver: torch.nan_to_num on K, pts3d, pts2d, weights, start (cer_solver.py:27-29) */
     LC_FLAG_TOL_NEEDS_SUCCESS = 2, /* solver: Ceres >= 2.1 "atleast_one_successful_step" guard (see oracle/lm_oracle.c) */
-    LC_FLAG_EXACT_HESSIAN = 4,     /* reserved: r * d2r term of hessian_6d_elem (pnp_auto.py:59-83); not implemented         */
+    LC_FLAG_EXACT_HESSIAN = 4,     /* pnp_jac_cov(_bwd): add the r * d2r term of hessian_6d_elem (pnp_auto.py:59-83); needs pts2d */
     LC_FLAG_FORCE_STREAMING = 8    /* per-pose entry points: always use the streaming fp64 kernel (tests / A-B comparisons)  */
 };
 

@@ -386,10 +386,27 @@ __device__ __forceinline__ void jac_setup(const lc_args& a, JacShared& s, int b)
     __syncthreads();
 }
 
+// Second-order term of hessian_6d_elem (pnp_auto.py:59-83): the reference's per-coordinate Hessian is
+// J J^T + r * d2r/d(delta)^2 with the exact exponential-map second derivative.  In the left basis
+//   d2r_a = -(1/z) (J'_a Z^T + Z J'_a^T) + blockdiag(S(D_a), 0),   Z = (q1, -q0, 0, 0, 0, 1),
+//   S(D)_ij = (D_i q_j + D_j q_i)/2 - delta_ij (D . q)            (i, j < 3),  D_a = J'_a[3:6]
+// (from d2 pi_a = -(1/z)(D e_z^T + e_z D^T) and d2(Exp(w) q)/dw_i dw_j = (e_i q_j + e_j q_i)/2 - delta_ij q).
+// Returns the packed-upper entry (i, j), i <= j.
+struct PointSecond { double q[3], iz, r[2]; };
+__device__ __forceinline__ double second_entry(const double (&J)[6], const PointSecond& p, int i, int j) {
+    const double Z[6] = {p.q[1], -p.q[0], 0.0, 0.0, 0.0, 1.0};
+    double v = -p.iz * (J[i] * Z[j] + Z[i] * J[j]);
+    if (i < 3 && j < 3) {
+        v += 0.5 * (J[3 + i] * p.q[j] + J[3 + j] * p.q[i]);
+        if (i == j) v -= J[3] * p.q[0] + J[4] * p.q[1] + J[5] * p.q[2];
+    }
+    return v;
+}
+
 // left-basis Jacobian rows from raw inputs (no projection error needed here)
 template <typename T>
 __device__ __forceinline__ void jac_point(const lc_args& a, const double* R, const double* t, const double* K, int b, int i,
-                                          double (&J)[2][6], double (&w)[2]) {
+                                          double (&J)[2][6], double (&w)[2], PointSecond* sec = nullptr) {
     const int64_t o3 = b * a.pts3d.stride[0] + i * a.pts3d.stride[1];
     const double X0 = ld<T>(a.pts3d, o3), X1 = ld<T>(a.pts3d, o3 + a.pts3d.stride[2]), X2 = ld<T>(a.pts3d, o3 + 2 * a.pts3d.stride[2]);
     const double q0 = fma(R[0], X0, fma(R[1], X1, R[2] * X2));
@@ -409,6 +426,13 @@ __device__ __forceinline__ void jac_point(const lc_args& a, const double* R, con
     const int64_t ow = b * a.weights.stride[0] + i * a.weights.stride[1];
     w[0] = ld<T>(a.weights, ow);
     w[1] = ld<T>(a.weights, ow + a.weights.stride[2]);
+    if (sec) {
+        // r = K[:2,:2] uv0 + K[:2,2] - pts2d   (residual_with_jac6d, pnp_auto.py:43-48)
+        const int64_t o2 = b * a.pts2d.stride[0] + i * a.pts2d.stride[1];
+        sec->q[0] = q0; sec->q[1] = q1; sec->q[2] = q2; sec->iz = iz;
+        sec->r[0] = fma(K[0], u0, fma(K[1], v0, K[2])) - ld<T>(a.pts2d, o2);
+        sec->r[1] = fma(K[3], u0, fma(K[4], v0, K[5])) - ld<T>(a.pts2d, o2 + a.pts2d.stride[2]);
+    }
 }
 
 template <typename T, int NT>
@@ -417,11 +441,24 @@ __device__ __forceinline__ void jac_hessian(const lc_args& a, JacShared& s, int 
     double acc[21];
 #pragma unroll
     for (int k = 0; k < 21; ++k) acc[k] = 0.0;
+    const bool exact = (a.flags & LC_FLAG_EXACT_HESSIAN) && a.pts2d.ptr;
     for (int i = tid; i < n; i += NT) {
         double J[2][6], w[2];
-        jac_point<T>(a, s.R, s.t, s.K, b, i, J, w);
+        PointSecond sec;
+        jac_point<T>(a, s.R, s.t, s.K, b, i, J, w, exact ? &sec : nullptr);
         acc_outer<0>(acc, w[0], J[0]);
         acc_outer<0>(acc, w[1], J[1]);
+        if (exact) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const double wr = w[c] * sec.r[c];
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int cc = r; cc < 6; ++cc) { acc[k] = fma(wr, second_entry(J[c], sec, r, cc), acc[k]); ++k; }
+            }
+        }
     }
     block_reduce<21, NT>(acc, s.red, s.fin);
     for (int e = tid; e < 36; e += NT) s.H[e] = tts_entry(s.fin, s.R, e / 6, e % 6);
@@ -523,9 +560,11 @@ __global__ void __launch_bounds__(NT) lc_jac_bwd_kernel(const lc_args a) {
         s.cHL[k] = v;
     }
     __syncthreads();
+    const bool exact = (a.flags & LC_FLAG_EXACT_HESSIAN) && a.pts2d.ptr;
     for (int i = tid; i < n; i += NT) {
         double J[2][6], w[2];
-        jac_point<T>(a, s.R, s.t, s.K, b, i, J, w);
+        PointSecond sec;
+        jac_point<T>(a, s.R, s.t, s.K, b, i, J, w, exact ? &sec : nullptr);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             double qh = 0.0;
@@ -533,7 +572,12 @@ __global__ void __launch_bounds__(NT) lc_jac_bwd_kernel(const lc_args a) {
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int cc = r; cc < 6; ++cc) { qh = fma(s.cHL[k], J[c][r] * J[c][cc], qh); ++k; }
+                for (int cc = r; cc < 6; ++cc) {
+                    double hk = J[c][r] * J[c][cc];
+                    if (exact) hk = fma(sec.r[c], second_entry(J[c], sec, r, cc), hk);
+                    qh = fma(s.cHL[k], hk, qh);
+                    ++k;
+                }
             double lin = 0.0;
 #pragma unroll
             for (int r = 0; r < 6; ++r) {

@@ -7,9 +7,9 @@ Hessians and 6 vmapped ``autograd.grad`` sweeps; here one kernel accumulates the
 inverts it and writes ``jac`` directly.  Like the reference it is differentiable w.r.t. ``weights``
 (a second kernel implements that backward).
 
-The Hessian is the Gauss-Newton one, ``sum_k W_k J_k J_k^T``; it equals the reference's
-``hessian_6d_elem`` exactly when ``pts2d`` is the re-projection of ``pts3d`` at ``state_gt``
-(residual 0), which is how ``Loss_cov_mixed`` calls it (``cov_mixed.py:120-121``).
+The Hessian is the reference's ``hessian_6d_elem``: ``sum_k W_k (J_k J_k^T + r_k d2r_k)`` with the exact
+exponential-map second derivative (closed form, see ``lc_stream.cu``); the second term vanishes when ``pts2d``
+is the re-projection of ``pts3d`` at ``state_gt``, which is how ``Loss_cov_mixed`` calls it (``cov_mixed.py:120-121``).
 """
 from __future__ import annotations
 
@@ -28,47 +28,47 @@ def _weights_as_bn2(weights: Tensor, B: int, N: int) -> Tensor:
     return weights.expand(B, N, 2)
 
 
-def _jac_cov_forward(pose, K, pts3d, weights, want_cov=True):
-    dev = nat.check_cuda(pose, K, pts3d, weights)
+def _jac_cov_forward(pose, K, pts3d, weights, pts2d=None):
+    dev = nat.check_cuda(pose, K, pts3d, weights, pts2d)
     dt = pts3d.dtype
     B, N = pts3d.shape[:2]
     jac = torch.empty(B, 6, N, 2, dtype=dt, device=dev)
     cov = torch.empty(B, 6, 6, dtype=dt, device=dev)
     flags = torch.empty(B, dtype=torch.int32, device=dev)
     args = nat.make_args(B, N, dt, K=K.to(dt).expand(B, 3, 3), pose=pose.to(dt).expand(B, 7), pts3d=pts3d,
-                         weights=weights.to(dt), jac=jac, cov=cov, lc_flags=flags)
+                         weights=weights.to(dt), pts2d=None if pts2d is None else pts2d.to(dt).expand(B, N, 2),
+                         jac=jac, cov=cov, lc_flags=flags, flags=0 if pts2d is None else nat.FLAG_EXACT_HESSIAN)
     nat.call("lc_b200_pnp_jac_cov", args, dev)
     return jac, cov, flags
 
 
 class _PnPJacCov(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weights, pose, K, pts3d):
-        jac, cov, flags = _jac_cov_forward(pose, K, pts3d, weights)
-        ctx.save_for_backward(weights, pose, K, pts3d)
+    def forward(ctx, weights, pose, K, pts3d, pts2d):
+        jac, cov, flags = _jac_cov_forward(pose, K, pts3d, weights, pts2d)
+        ctx.save_for_backward(weights, pose, K, pts3d, pts2d)
         ctx.mark_non_differentiable(flags)
         return jac, cov, flags
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_jac, g_cov, _g_flags):
-        weights, pose, K, pts3d = ctx.saved_tensors
+        weights, pose, K, pts3d, pts2d = ctx.saved_tensors
         dev, dt = pts3d.device, pts3d.dtype
         B, N = pts3d.shape[:2]
         gw = torch.empty(B, N, 2, dtype=dt, device=dev)
         if g_jac is None:
             g_jac = torch.zeros(B, 6, N, 2, dtype=dt, device=dev)
         args = nat.make_args(B, N, dt, K=K.to(dt).expand(B, 3, 3), pose=pose.to(dt).expand(B, 7), pts3d=pts3d,
-                             weights=weights.to(dt), g_jac=g_jac.to(dt), g_cov=None if g_cov is None else g_cov.to(dt),
-                             g_weights=gw)
+                             weights=weights.to(dt), pts2d=pts2d.to(dt).expand(B, N, 2), g_jac=g_jac.to(dt),
+                             g_cov=None if g_cov is None else g_cov.to(dt), g_weights=gw, flags=nat.FLAG_EXACT_HESSIAN)
         nat.call("lc_b200_pnp_jac_cov_bwd", args, dev)
-        return gw.sum_to_size(weights.shape) if gw.shape != weights.shape else gw, None, None, None
+        return gw.sum_to_size(weights.shape) if gw.shape != weights.shape else gw, None, None, None, None
 
 
 def weighted_pnp_jac_wrt_pts2d(pts2d: Tensor, state_gt: Tensor, cam_K: Tensor, pts3d: Tensor, weights: Tensor,
                                with_cov: bool = False):
-    """Reference signature (``pnp_auto.py:111``).  ``pts2d`` is accepted for signature parity; the
-    Gauss-Newton Jacobian does not depend on it (see module docstring)."""
+    """Reference signature (``pnp_auto.py:111``)."""
     batched = pts3d.dim() != 2
     p3 = pts3d.detach() if batched else pts3d.detach().unsqueeze(0)
     p3 = p3.reshape((-1,) + tuple(p3.shape[-2:]))
@@ -78,7 +78,8 @@ def weighted_pnp_jac_wrt_pts2d(pts2d: Tensor, state_gt: Tensor, cam_K: Tensor, p
     w = _weights_as_bn2(w.reshape((B,) + tuple(w.shape[len(lead) if batched else 1:])), B, N)
     pose = state_gt.detach().reshape(-1, 7).expand(B, 7)
     K = cam_K.detach().reshape(-1, 3, 3).expand(B, 3, 3)
-    jac, cov, _ = _PnPJacCov.apply(w, pose, K, p3)
+    p2 = (pts2d.detach() if batched else pts2d.detach().unsqueeze(0)).expand(tuple(lead) + (N, 2) if batched else (1, N, 2)).reshape(B, N, 2)
+    jac, cov, _ = _PnPJacCov.apply(w, pose, K, p3, p2)
     jac = jac.reshape(lead + (6, N, 2))
     cov = cov.reshape(lead + (6, 6))
     return (jac, cov) if with_cov else jac
@@ -94,7 +95,8 @@ def diff_pnp_perturb(quat_xyz: Tensor, cam_K: Tensor, pts3d: Tensor, pts2d: Tens
     p3 = pts3d.detach().reshape((-1,) + tuple(pts3d.shape[-2:]))
     B, N = p3.shape[:2]
     _, _, flags = _jac_cov_forward(quat_xyz.detach().reshape(-1, 7), cam_K.detach().reshape(-1, 3, 3), p3,
-                                   _weights_as_bn2(icov2.detach().reshape((B,) + tuple(icov2.shape[len(lead):])), B, N))
+                                   _weights_as_bn2(icov2.detach().reshape((B,) + tuple(icov2.shape[len(lead):])), B, N),
+                                   pts2d.detach().expand(tuple(lead) + (N, 2)).reshape(B, N, 2))
     info = (flags & nat.ST_HESS_NOT_SPD).reshape(lead)
     update = cov.new_zeros(lead + (6,))
     return info, update, (cov if with_cov else None)

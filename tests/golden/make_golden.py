@@ -87,8 +87,29 @@ def run_reference(d, max_err_len=32, rel_thresh=3, w_e_thresh=4):
                 jac=jac.detach(), cov=cov.detach())
 
 
+def make_jac_exact():
+    """weighted_pnp_jac_wrt_pts2d AWAY from the optimum (measured pts2d, residual != 0): exercises the r * d2r term
+    of hessian_6d_elem (pnp_auto.py:59-83) and the double-backward w.r.t. the weights (:129-134)."""
+    c = make_correspondences(3, 40, 77)
+    r32 = lambda t: t.to(torch.float32).to(torch.float64)
+    K, pose, X, x = r32(c.K), r32(c.pose), r32(c.pts3d), r32(c.pts2d)
+    W = r32(c.inv_std ** 2).requires_grad_(True)
+    g = torch.Generator().manual_seed(5)
+    Gj = torch.randn(3, 6, 40, 2, generator=g, dtype=torch.float64)
+    Gc = torch.randn(3, 6, 6, generator=g, dtype=torch.float64)
+    jac, cov = pnp_auto.weighted_pnp_jac_wrt_pts2d(x, pose, K, X, W, with_cov=True)
+    gW, = torch.autograd.grad((jac * Gj).sum() + (cov * Gc).sum(), W)
+    path = os.path.join(HERE, "jacx_b3_n40.npz")
+    np.savez_compressed(path, in_K=K.numpy().astype(np.float32), in_pose=pose.numpy().astype(np.float32),
+                        in_pts3d=X.numpy().astype(np.float32), in_pts2d=x.numpy().astype(np.float32),
+                        in_W=W.detach().numpy().astype(np.float32), Gj=Gj.numpy(), Gc=Gc.numpy(),
+                        ref_jac=jac.detach().numpy(), ref_cov=cov.detach().numpy(), ref_gW=gW.numpy())
+    print("jacx_b3_n40:", os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    make_jac_exact()
     for name, B, N, seed, vmode, regime, store_jac in CASES:
         d = build_inputs(B, N, seed, vmode, regime)
         o = run_reference(d)

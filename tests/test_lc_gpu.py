@@ -130,12 +130,25 @@ def test_non_spd_hessian_falls_back_to_identity(oracle):
     assert rel_err(o["g_inv_std"].cpu().numpy()[1:], ref["g_inv_std"][1:]) <= 1e-9
 
 
+def _ref_project(K, pose, X):
+    """project_apply(K, X, *quaternion_rep_to_RT(pose)) of the reference (transforms.py:47-63, 2/|q| scaling included)."""
+    r, i, j, k = pose[:, 0], pose[:, 1], pose[:, 2], pose[:, 3]
+    two_s = 2.0 / pose[:, :4].norm(dim=-1)
+    R = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1).reshape(-1, 3, 3)
+    P = (X @ R.mT + pose[:, None, 4:]) @ K.mT
+    return P[..., :2] / P[..., 2:].clamp(min=0.1)
+
+
 @pytest.mark.parametrize("name", [n for n in golden_files() if "n4096" not in n and "heavy" not in n])
 def test_pnp_jac_cov_matches_reference_golden(name):
+    """As Loss_cov_mixed calls it (cov_mixed.py:120-121): pts2d = the re-projection, weights = the robust weights."""
     from lc_b200.nll.pnp_auto import weighted_pnp_jac_wrt_pts2d
     g = load_golden(name)
     dt = torch.float64
-    jac, cov = weighted_pnp_jac_wrt_pts2d(_cuda(g["in_pts2d"], dt), _cuda(g["in_pose"], dt), _cuda(g["in_K"], dt),
+    proj = _ref_project(_cuda(g["in_K"], dt), _cuda(g["in_pose"], dt), _cuda(g["in_pts3d"], dt))
+    jac, cov = weighted_pnp_jac_wrt_pts2d(proj, _cuda(g["in_pose"], dt), _cuda(g["in_K"], dt),
                                           _cuda(g["in_pts3d"], dt), _cuda(g["ref_W"], dt), with_cov=True)
     assert jac.shape == g["ref_jac"].shape and cov.shape == (len(jac), 6, 6)
     tol = 1e-6 if "init" in name else 2e-7     # | |q| - 1 | of the fp32-rounded fixture quaternions, see above
@@ -205,3 +218,25 @@ def test_tma_and_cp_async_staging_agree():
         f0 = solve_and_loss(c.K, c.start, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
         f1 = solve_and_loss(c.K, c.start, planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std), None, c.bbox_3d)
         assert torch.equal(f0["states"], f1["states"]) and torch.equal(f0["loss"], f1["loss"])
+
+
+def test_pnp_jac_exact_hessian_away_from_optimum():
+    """weighted_pnp_jac_wrt_pts2d with measured pts2d (residual != 0): the reference's per-coordinate Hessian carries
+    r * d2r (hessian_6d_elem, pnp_auto.py:59-83).  Fixture generated by the unmodified reference: jac, cov and the
+    gradient w.r.t. the weights of <jac, Gj> + <cov, Gc>."""
+    from lc_b200.nll.pnp_auto import weighted_pnp_jac_wrt_pts2d
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "jacx_b3_n40.npz"))
+    dt = torch.float64
+    W = _cuda(z["in_W"], dt).requires_grad_(True)
+    jac, cov = weighted_pnp_jac_wrt_pts2d(_cuda(z["in_pts2d"], dt), _cuda(z["in_pose"], dt), _cuda(z["in_K"], dt),
+                                          _cuda(z["in_pts3d"], dt), W, with_cov=True)
+    assert rel_err(jac.detach().cpu().numpy(), z["ref_jac"]) <= 2e-7
+    assert rel_err(cov.detach().cpu().numpy(), z["ref_cov"]) <= 2e-7
+    ((jac * _cuda(z["Gj"], dt)).sum() + (cov * _cuda(z["Gc"], dt)).sum()).backward()
+    assert rel_err(W.grad.cpu().numpy(), z["ref_gW"]) <= 1e-6
+    # and the Gauss-Newton version (no pts2d dependence) must differ measurably here, i.e. the term matters
+    from lc_b200.nll.pnp_auto import _jac_cov_forward
+    j0, c0, _ = _jac_cov_forward(_cuda(z["in_pose"], dt), _cuda(z["in_K"], dt), _cuda(z["in_pts3d"], dt), W.detach())
+    assert rel_err(c0.cpu().numpy(), z["ref_cov"]) > 1e-5
