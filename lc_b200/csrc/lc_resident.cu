@@ -152,6 +152,216 @@ __device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s
     block_reduce<28, NT>(acc, s.red, s.fin);
 }
 
+// ---------------------------------------------------------------------------------------------
+// LC phase on the staged arrays (A = X -> q, B = x -> ec), shared by the resident kernel and the dense-producer kernel
+// (lc_dense.cu).  WSrc supplies the inverse-std weights of point i, Sink receives the per-point gradients.
+// ---------------------------------------------------------------------------------------------
+struct DirectWeights {   // weights streamed from a strided (N,2) view (L2 resident after the first touch)
+    const float* p;
+    int64_t sn, sc;
+    __device__ __forceinline__ void get(int i, float& s0, float& s1) const { s0 = p[i * sn]; s1 = p[i * sn + sc]; }
+};
+struct DirectSink {      // gradients written to the strided views of lc_args
+    const lc_args& a;
+    int b;
+    __device__ __forceinline__ bool want_any() const { return a.g_pts3d.ptr || a.g_pts2d.ptr || a.g_weights.ptr; }
+    __device__ __forceinline__ bool want_pts3d() const { return a.g_pts3d.ptr != nullptr; }
+    __device__ __forceinline__ void weight_grad(int i, int c, float g, float) const {
+        if (a.g_weights.ptr) stf(a.g_weights, b * a.g_weights.stride[0] + i * a.g_weights.stride[1] + c * a.g_weights.stride[2], g);
+    }
+    __device__ __forceinline__ void pts2d_grad(int i, int c, float g) const {
+        if (a.g_pts2d.ptr) stf(a.g_pts2d, b * a.g_pts2d.stride[0] + i * a.g_pts2d.stride[1] + c * a.g_pts2d.stride[2], g);
+    }
+    __device__ __forceinline__ void pts3d_grad(int i, float g0, float g1, float g2) const {
+        const int64_t o = b * a.g_pts3d.stride[0] + i * a.g_pts3d.stride[1];
+        stf(a.g_pts3d, o, g0); stf(a.g_pts3d, o + a.g_pts3d.stride[2], g1); stf(a.g_pts3d, o + 2 * a.g_pts3d.stride[2], g2);
+    }
+};
+
+template <int NT, class WSrc, class Sink>
+__device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, const WSrc& wsrc, Sink& sink) {
+    const int tid = threadIdx.x;
+    if (tid == 0) lc_pose_setup(s, true);
+    __syncthreads();
+
+    const int64_t ovb = a.valid.ptr ? b * a.valid.stride[0] : 0;
+    // pass 1 (fp64): P = R X + t, project_apply + clamp_error once per point; P, ec kept as fp32 in place
+    {
+        const double Lmax = a.max_err_len;
+        const double lim = Lmax - 1e-6, lim2 = lim > 0.0 ? lim * lim : -1.0;   // |e|+1e-6 > Lmax  <=>  |e|^2 > lim2
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i], x0 = l.B0[i], x1 = l.B1[i];
+            const double q0 = fma(s.R[0], X0, fma(s.R[1], X1, s.R[2] * X2));
+            const double q1 = fma(s.R[3], X0, fma(s.R[4], X1, s.R[5] * X2));
+            const double q2 = fma(s.R[6], X0, fma(s.R[7], X1, s.R[8] * X2));
+            const double P0 = q0 + s.t[0], P1 = q1 + s.t[1], P2 = q2 + s.t[2];
+            const double KP0 = fma(s.K[0], P0, fma(s.K[1], P1, s.K[2] * P2));
+            const double KP1 = fma(s.K[3], P0, fma(s.K[4], P1, s.K[5] * P2));
+            const double KP2 = fma(s.K[6], P0, fma(s.K[7], P1, s.K[8] * P2));
+            const double iz = fast_rcp(KP2 > 0.1 ? KP2 : 0.1);
+            double e0 = fma(-KP0, iz, x0), e1 = fma(-KP1, iz, x1);
+            const double l2 = fma(e0, e0, e1 * e1);
+            if (l2 > lim2) {
+                const double len = sqrt(l2) + 1e-6;
+                const double f = (len - Lmax) / len;
+                e0 = fma(-f, e0, e0);
+                e1 = fma(-f, e1, e1);
+            }
+            const float ec0 = static_cast<float>(e0), ec1 = static_cast<float>(e1);
+            // q = R X is what is cached (not P = q + t): q x D then keeps fp32 relative precision even when |X| << |t|
+            l.A0[i] = static_cast<float>(q0); l.A1[i] = static_cast<float>(q1); l.A2[i] = static_cast<float>(q2);
+            l.B0[i] = ec0; l.B1[i] = ec1;
+            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
+            acc0 = fmaf(v, fabsf(ec0), acc0); acc1 = fmaf(v, fabsf(ec1), acc1); acc2 += v;
+        }
+        double acc[3] = {acc0, acc1, acc2};
+        block_reduce<3, NT>(acc, s.red, s.fin);
+    }
+    const double vcnt = a.valid.ptr ? s.fin[2] : static_cast<double>(n);
+    const float d0 = static_cast<float>(a.rel_thresh * (s.fin[0] / vcnt)), d1 = static_cast<float>(a.rel_thresh * (s.fin[1] / vcnt));
+    __syncthreads();
+    // pass 2 (fp32): q_a = mean valid s^2 sigma
+    {
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            float s0, s1;
+            wsrc.get(i, s0, s1);
+            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
+            const float a0 = fabsf(l.B0[i]), a1 = fabsf(l.B1[i]);
+            const float sg0 = a0 > d0 ? d0 * (2.f * a0 - d0) : a0 * a0;
+            const float sg1 = a1 > d1 ? d1 * (2.f * a1 - d1) : a1 * a1;
+            acc0 = fmaf(v * (s0 * s0), sg0, acc0);
+            acc1 = fmaf(v * (s1 * s1), sg1, acc1);
+        }
+        double acc[2] = {acc0, acc1};
+        block_reduce<2, NT>(acc, s.red, s.fin);
+    }
+    // delta_k = sqrt(we * q_a / (sigma_k + 1e-6)) = sq_a * rsqrt(sigma_k + 1e-6)
+    const float sq0 = static_cast<float>(sqrt((s.fin[0] / vcnt) * a.w_e_thresh)), sq1 = static_cast<float>(sqrt((s.fin[1] / vcnt) * a.w_e_thresh));
+    __syncthreads();
+
+    const float t0 = static_cast<float>(s.t[0]), t1 = static_cast<float>(s.t[1]), t2 = static_cast<float>(s.t[2]);
+    const float k00 = static_cast<float>(s.K[0]), k01 = static_cast<float>(s.K[1]), k10 = static_cast<float>(s.K[3]), k11 = static_cast<float>(s.K[4]);
+    // Depth-decoupled accumulation basis.  For an object that is small compared to its depth every point has nearly
+    // the same normalised image position uv0, so the t_z Jacobian column D_z = -K uv0 / z is nearly a fixed combination
+    // of the t_x, t_y columns and H is ill conditioned (cond ~ (z/size)^2: the depth ambiguity).  The sums are therefore
+    // taken with the column t_z' = t_z + uc t_x + vc t_y, (uc, vc) = t_xy / t_z, whose entries
+    //   D_z + uc D_x + vc D_y = K (uvc - uv0) / z = K (uvc q_z - q_xy) / z^2
+    // are formed from the small vector q directly (no cancellation), and mapped back in fp64 (PoseShared::Tm).
+    const float uc = static_cast<float>(s.t[0] / s.t[2]), vc = static_cast<float>(s.t[1] / s.t[2]);
+
+    // per-point fp32 geometry shared by passes 3 and 4: left-basis Jacobian rows and robust weights
+    auto point_terms = [&](int i, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2], float (&w)[2]) {
+        const float q0 = l.A0[i], q1 = l.A1[i], q2 = l.A2[i];
+        const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
+        ec[0] = l.B0[i]; ec[1] = l.B1[i];
+        wsrc.get(i, sk[0], sk[1]);
+        const float iz = __fdividef(1.f, P2);
+        const float u0 = P0 * iz, v0 = P1 * iz;
+        const float du0 = fmaf(uc, q2, -q0) * iz, dv0 = fmaf(vc, q2, -q1) * iz;   // uvc - uv0
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float ka = c ? k10 : k00, kb = c ? k11 : k01;
+            const float e0 = ka * iz, e1 = kb * iz, e2 = -fmaf(ka, u0, kb * v0) * iz;
+            J[c][0] = fmaf(q1, e2, -q2 * e1);
+            J[c][1] = fmaf(q2, e0, -q0 * e2);
+            J[c][2] = fmaf(q0, e1, -q1 * e0);
+            J[c][3] = e0; J[c][4] = e1; J[c][5] = fmaf(ka, du0, kb * dv0) * iz;
+            const float dc = c ? d1 : d0, sq = c ? sq1 : sq0;
+            const float av = fabsf(ec[c]);
+            sg[c] = av > dc ? dc * (2.f * av - dc) : av * av;
+            del[c] = sq * rsqrtf(sg[c] + 1e-6f);
+            w[c] = sk[c] > del[c] ? del[c] * (2.f * sk[c] - del[c]) : sk[c] * sk[c];
+        }
+    };
+
+    // pass 3 (fp32 partial sums, fp64 CTA reduction): H' = sum W J'J'^T, G' = sum W^2 sigma J'J'^T, b' = sum W ec J'
+    {
+        float acc[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, J, ec, sk, sg, del, w);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                acc_outer<0>(acc, w[c], J[c]);
+                acc_outer<21>(acc, w[c] * w[c] * sg[c], J[c]);
+                const float wb = w[c] * ec[c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[42 + r] = fmaf(wb, J[c][r], acc[42 + r]);
+            }
+        }
+        double accd[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) accd[k] = acc[k];
+        block_reduce<48, NT>(accd, s.red, s.fin);
+    }
+    lc_six_forward<float, NT>(a, s, b);
+    if (!sink.want_any()) return;
+    lc_six_backward<NT>(s);
+
+    // pass 4 (fp32): per-coordinate adjoints (SURVEY §8a) and the three input gradients
+    {
+        float cH[kSym], cG[kSym], bL[6];
+#pragma unroll
+        for (int k = 0; k < kSym; ++k) { cH[k] = static_cast<float>(s.cHL[k]); cG[k] = static_cast<float>(s.cGL[k]); }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bL[k] = static_cast<float>(s.bL[k]);
+        const float K0 = static_cast<float>(s.K[0]), K1 = static_cast<float>(s.K[1]), K2 = static_cast<float>(s.K[2]);
+        const float K3 = static_cast<float>(s.K[3]), K4 = static_cast<float>(s.K[4]), K5 = static_cast<float>(s.K[5]);
+        const float K6 = static_cast<float>(s.K[6]), K7 = static_cast<float>(s.K[7]), K8 = static_cast<float>(s.K[8]);
+        float Rf[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
+        for (int i = tid; i < n; i += NT) {
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, J, ec, sk, sg, del, w);
+            float ecb[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float qh = 0.f, qg = 0.f, lb = 0.f;
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    lb = fmaf(J[c][r], bL[r], lb);
+#pragma unroll
+                    for (int cc = r; cc < 6; ++cc) {
+                        const float pp = J[c][r] * J[c][cc];
+                        qh = fmaf(cH[k], pp, qh);
+                        qg = fmaf(cG[k], pp, qg);
+                        ++k;
+                    }
+                }
+                const float Wbar = qh + 2.f * w[c] * sg[c] * qg + ec[c] * lb;
+                const float sigbar = w[c] * w[c] * qg;
+                sink.weight_grad(i, c, Wbar * (sk[c] > del[c] ? 2.f * del[c] : 2.f * sk[c]), sk[c]);
+                const float dc = c ? d1 : d0;
+                const float av = fabsf(ec[c]);
+                const float sgn = (ec[c] > 0.f) ? 1.f : ((ec[c] < 0.f) ? -1.f : 0.f);
+                ecb[c] = sigbar * (av > dc ? 2.f * dc : 2.f * av) * sgn;
+                sink.pts2d_grad(i, c, ecb[c]);
+            }
+            if (sink.want_pts3d()) {
+                // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
+                const float P0 = l.A0[i] + t0, P1 = l.A1[i] + t1, P2 = l.A2[i] + t2;
+                const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
+                const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
+                const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
+                const bool act = KP2 >= 0.1f;
+                const float iz = __fdividef(1.f, act ? KP2 : 0.1f);
+                const float pr0 = act ? KP0 * iz : 0.f, pr1 = act ? KP1 * iz : 0.f;   // proj * [z >= 0.1]
+                const float gP0 = (fmaf(-pr0, K6, K0) * ecb[0] + fmaf(-pr1, K6, K3) * ecb[1]) * iz;
+                const float gP1 = (fmaf(-pr0, K7, K1) * ecb[0] + fmaf(-pr1, K7, K4) * ecb[1]) * iz;
+                const float gP2 = (fmaf(-pr0, K8, K2) * ecb[0] + fmaf(-pr1, K8, K5) * ecb[1]) * iz;
+                sink.pts3d_grad(i, -(Rf[0] * gP0 + Rf[3] * gP1 + Rf[6] * gP2), -(Rf[1] * gP0 + Rf[4] * gP1 + Rf[7] * gP2),
+                                -(Rf[2] * gP0 + Rf[5] * gP1 + Rf[8] * gP2));
+            }
+        }
+    }
+}
+
 template <int NT, int MODE>
 __global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -249,193 +459,9 @@ __global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int
     if (!(MODE & MODE_LC)) return;
 
     // =========================== LC loss ===========================
-    if (tid == 0) lc_pose_setup(s, true);
-    __syncthreads();
-
-    const int64_t owb = b * a.weights.stride[0];
-    const int64_t ovb = a.valid.ptr ? b * a.valid.stride[0] : 0;
-    // pass 1 (fp64): P = R X + t, project_apply + clamp_error once per point; P, ec kept as fp32 in place
-    {
-        const double Lmax = a.max_err_len;
-        const double lim = Lmax - 1e-6, lim2 = lim > 0.0 ? lim * lim : -1.0;   // |e|+1e-6 > Lmax  <=>  |e|^2 > lim2
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-        for (int i = tid; i < n; i += NT) {
-            const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i], x0 = l.B0[i], x1 = l.B1[i];
-            const double q0 = fma(s.R[0], X0, fma(s.R[1], X1, s.R[2] * X2));
-            const double q1 = fma(s.R[3], X0, fma(s.R[4], X1, s.R[5] * X2));
-            const double q2 = fma(s.R[6], X0, fma(s.R[7], X1, s.R[8] * X2));
-            const double P0 = q0 + s.t[0], P1 = q1 + s.t[1], P2 = q2 + s.t[2];
-            const double KP0 = fma(s.K[0], P0, fma(s.K[1], P1, s.K[2] * P2));
-            const double KP1 = fma(s.K[3], P0, fma(s.K[4], P1, s.K[5] * P2));
-            const double KP2 = fma(s.K[6], P0, fma(s.K[7], P1, s.K[8] * P2));
-            const double iz = fast_rcp(KP2 > 0.1 ? KP2 : 0.1);
-            double e0 = fma(-KP0, iz, x0), e1 = fma(-KP1, iz, x1);
-            const double l2 = fma(e0, e0, e1 * e1);
-            if (l2 > lim2) {
-                const double len = sqrt(l2) + 1e-6;
-                const double f = (len - Lmax) / len;
-                e0 = fma(-f, e0, e0);
-                e1 = fma(-f, e1, e1);
-            }
-            const float ec0 = static_cast<float>(e0), ec1 = static_cast<float>(e1);
-            // q = R X is what is cached (not P = q + t): q x D then keeps fp32 relative precision even when |X| << |t|
-            l.A0[i] = static_cast<float>(q0); l.A1[i] = static_cast<float>(q1); l.A2[i] = static_cast<float>(q2);
-            l.B0[i] = ec0; l.B1[i] = ec1;
-            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
-            acc0 = fmaf(v, fabsf(ec0), acc0); acc1 = fmaf(v, fabsf(ec1), acc1); acc2 += v;
-        }
-        double acc[3] = {acc0, acc1, acc2};
-        block_reduce<3, NT>(acc, s.red, s.fin);
-    }
-    const double vcnt = a.valid.ptr ? s.fin[2] : static_cast<double>(n);
-    const float d0 = static_cast<float>(a.rel_thresh * (s.fin[0] / vcnt)), d1 = static_cast<float>(a.rel_thresh * (s.fin[1] / vcnt));
-    __syncthreads();
-    // pass 2 (fp32): q_a = mean valid s^2 sigma
-    {
-        float acc0 = 0.f, acc1 = 0.f;
-        for (int i = tid; i < n; i += NT) {
-            float s0, s1;
-            if (RAW) { s0 = l.S0[i]; s1 = l.S1[i]; }
-            else { const int64_t ow = owb + i * a.weights.stride[1]; s0 = ldf(a.weights, ow); s1 = ldf(a.weights, ow + a.weights.stride[2]); }
-            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
-            const float a0 = fabsf(l.B0[i]), a1 = fabsf(l.B1[i]);
-            const float sg0 = a0 > d0 ? d0 * (2.f * a0 - d0) : a0 * a0;
-            const float sg1 = a1 > d1 ? d1 * (2.f * a1 - d1) : a1 * a1;
-            acc0 = fmaf(v * (s0 * s0), sg0, acc0);
-            acc1 = fmaf(v * (s1 * s1), sg1, acc1);
-        }
-        double acc[2] = {acc0, acc1};
-        block_reduce<2, NT>(acc, s.red, s.fin);
-    }
-    // delta_k = sqrt(we * q_a / (sigma_k + 1e-6)) = sq_a * rsqrt(sigma_k + 1e-6)
-    const float sq0 = static_cast<float>(sqrt((s.fin[0] / vcnt) * a.w_e_thresh)), sq1 = static_cast<float>(sqrt((s.fin[1] / vcnt) * a.w_e_thresh));
-    __syncthreads();
-
-    const float t0 = static_cast<float>(s.t[0]), t1 = static_cast<float>(s.t[1]), t2 = static_cast<float>(s.t[2]);
-    const float k00 = static_cast<float>(s.K[0]), k01 = static_cast<float>(s.K[1]), k10 = static_cast<float>(s.K[3]), k11 = static_cast<float>(s.K[4]);
-    // Depth-decoupled accumulation basis.  For an object that is small compared to its depth every point has nearly
-    // the same normalised image position uv0, so the t_z Jacobian column D_z = -K uv0 / z is nearly a fixed combination
-    // of the t_x, t_y columns and H is ill conditioned (cond ~ (z/size)^2: the depth ambiguity).  The sums are therefore
-    // taken with the column t_z' = t_z + uc t_x + vc t_y, (uc, vc) = t_xy / t_z, whose entries
-    //   D_z + uc D_x + vc D_y = K (uvc - uv0) / z = K (uvc q_z - q_xy) / z^2
-    // are formed from the small vector q directly (no cancellation), and mapped back in fp64 (PoseShared::Tm).
-    const float uc = static_cast<float>(s.t[0] / s.t[2]), vc = static_cast<float>(s.t[1] / s.t[2]);
-
-    // per-point fp32 geometry shared by passes 3 and 4: left-basis Jacobian rows and robust weights
-    auto point_terms = [&](int i, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2], float (&w)[2]) {
-        const float q0 = l.A0[i], q1 = l.A1[i], q2 = l.A2[i];
-        const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
-        ec[0] = l.B0[i]; ec[1] = l.B1[i];
-        if (RAW) { sk[0] = l.S0[i]; sk[1] = l.S1[i]; }
-        else { const int64_t ow = owb + i * a.weights.stride[1]; sk[0] = ldf(a.weights, ow); sk[1] = ldf(a.weights, ow + a.weights.stride[2]); }
-        const float iz = __fdividef(1.f, P2);
-        const float u0 = P0 * iz, v0 = P1 * iz;
-        const float du0 = fmaf(uc, q2, -q0) * iz, dv0 = fmaf(vc, q2, -q1) * iz;   // uvc - uv0
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const float ka = c ? k10 : k00, kb = c ? k11 : k01;
-            const float e0 = ka * iz, e1 = kb * iz, e2 = -fmaf(ka, u0, kb * v0) * iz;
-            J[c][0] = fmaf(q1, e2, -q2 * e1);
-            J[c][1] = fmaf(q2, e0, -q0 * e2);
-            J[c][2] = fmaf(q0, e1, -q1 * e0);
-            J[c][3] = e0; J[c][4] = e1; J[c][5] = fmaf(ka, du0, kb * dv0) * iz;
-            const float dc = c ? d1 : d0, sq = c ? sq1 : sq0;
-            const float av = fabsf(ec[c]);
-            sg[c] = av > dc ? dc * (2.f * av - dc) : av * av;
-            del[c] = sq * rsqrtf(sg[c] + 1e-6f);
-            w[c] = sk[c] > del[c] ? del[c] * (2.f * sk[c] - del[c]) : sk[c] * sk[c];
-        }
-    };
-
-    // pass 3 (fp32 partial sums, fp64 CTA reduction): H' = sum W J'J'^T, G' = sum W^2 sigma J'J'^T, b' = sum W ec J'
-    {
-        float acc[48];
-#pragma unroll
-        for (int k = 0; k < 48; ++k) acc[k] = 0.f;
-        for (int i = tid; i < n; i += NT) {
-            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
-            point_terms(i, J, ec, sk, sg, del, w);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                acc_outer<0>(acc, w[c], J[c]);
-                acc_outer<21>(acc, w[c] * w[c] * sg[c], J[c]);
-                const float wb = w[c] * ec[c];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) acc[42 + r] = fmaf(wb, J[c][r], acc[42 + r]);
-            }
-        }
-        double accd[48];
-#pragma unroll
-        for (int k = 0; k < 48; ++k) accd[k] = acc[k];
-        block_reduce<48, NT>(accd, s.red, s.fin);
-    }
-    lc_six_forward<float, NT>(a, s, b);
-    const bool want_grads = a.g_pts3d.ptr || a.g_pts2d.ptr || a.g_weights.ptr;
-    if (!want_grads) return;
-    lc_six_backward<NT>(s);
-
-    // pass 4 (fp32): per-coordinate adjoints (SURVEY §8a) and the three input gradients
-    {
-        float cH[kSym], cG[kSym], bL[6];
-#pragma unroll
-        for (int k = 0; k < kSym; ++k) { cH[k] = static_cast<float>(s.cHL[k]); cG[k] = static_cast<float>(s.cGL[k]); }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) bL[k] = static_cast<float>(s.bL[k]);
-        const float K0 = static_cast<float>(s.K[0]), K1 = static_cast<float>(s.K[1]), K2 = static_cast<float>(s.K[2]);
-        const float K3 = static_cast<float>(s.K[3]), K4 = static_cast<float>(s.K[4]), K5 = static_cast<float>(s.K[5]);
-        const float K6 = static_cast<float>(s.K[6]), K7 = static_cast<float>(s.K[7]), K8 = static_cast<float>(s.K[8]);
-        float Rf[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
-        const int64_t gwb = b * a.g_weights.stride[0], g2b = b * a.g_pts2d.stride[0], g3b = b * a.g_pts3d.stride[0];
-        for (int i = tid; i < n; i += NT) {
-            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
-            point_terms(i, J, ec, sk, sg, del, w);
-            float ecb[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float qh = 0.f, qg = 0.f, lb = 0.f;
-                int k = 0;
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    lb = fmaf(J[c][r], bL[r], lb);
-#pragma unroll
-                    for (int cc = r; cc < 6; ++cc) {
-                        const float pp = J[c][r] * J[c][cc];
-                        qh = fmaf(cH[k], pp, qh);
-                        qg = fmaf(cG[k], pp, qg);
-                        ++k;
-                    }
-                }
-                const float Wbar = qh + 2.f * w[c] * sg[c] * qg + ec[c] * lb;
-                const float sigbar = w[c] * w[c] * qg;
-                if (a.g_weights.ptr)
-                    stf(a.g_weights, gwb + i * a.g_weights.stride[1] + c * a.g_weights.stride[2], Wbar * (sk[c] > del[c] ? 2.f * del[c] : 2.f * sk[c]));
-                const float dc = c ? d1 : d0;
-                const float av = fabsf(ec[c]);
-                const float sgn = (ec[c] > 0.f) ? 1.f : ((ec[c] < 0.f) ? -1.f : 0.f);
-                ecb[c] = sigbar * (av > dc ? 2.f * dc : 2.f * av) * sgn;
-                if (a.g_pts2d.ptr) stf(a.g_pts2d, g2b + i * a.g_pts2d.stride[1] + c * a.g_pts2d.stride[2], ecb[c]);
-            }
-            if (a.g_pts3d.ptr) {
-                // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
-                const float P0 = l.A0[i] + t0, P1 = l.A1[i] + t1, P2 = l.A2[i] + t2;
-                const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
-                const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
-                const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
-                const bool act = KP2 >= 0.1f;
-                const float iz = __fdividef(1.f, act ? KP2 : 0.1f);
-                const float pr0 = act ? KP0 * iz : 0.f, pr1 = act ? KP1 * iz : 0.f;   // proj * [z >= 0.1]
-                const float gP0 = (fmaf(-pr0, K6, K0) * ecb[0] + fmaf(-pr1, K6, K3) * ecb[1]) * iz;
-                const float gP1 = (fmaf(-pr0, K7, K1) * ecb[0] + fmaf(-pr1, K7, K4) * ecb[1]) * iz;
-                const float gP2 = (fmaf(-pr0, K8, K2) * ecb[0] + fmaf(-pr1, K8, K5) * ecb[1]) * iz;
-                const int64_t o = g3b + i * a.g_pts3d.stride[1];
-                stf(a.g_pts3d, o, -(Rf[0] * gP0 + Rf[3] * gP1 + Rf[6] * gP2));
-                stf(a.g_pts3d, o + a.g_pts3d.stride[2], -(Rf[1] * gP0 + Rf[4] * gP1 + Rf[7] * gP2));
-                stf(a.g_pts3d, o + 2 * a.g_pts3d.stride[2], -(Rf[2] * gP0 + Rf[5] * gP1 + Rf[8] * gP2));
-            }
-        }
-    }
+    const DirectWeights wsrc{static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0], a.weights.stride[1], a.weights.stride[2]};
+    DirectSink sink{a, b};
+    lc_phase_res<NT>(a, s, l, b, n, wsrc, sink);
 }
 
 // ---------------------------------------------------------------------------------------------
