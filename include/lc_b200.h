@@ -114,6 +114,38 @@ typedef struct lc_args {
                            all-reduce a batch-sharded mean needs (losses.py:334,386), or NULL */
 } lc_args;
 
+/*
+ * Dense producer fused with the LC loss ("next" row f1 of SURVEY.md §8): replaces, for the gdr-net structure, the glue of
+ * Loss_fn.dense_pose_loss (losses.py:336-386) in front of Loss_cov_mixed and its autograd backward:
+ *   weights  = softmax(all 2*H*W weight logits of a sample) * weights_scale            (losses.py:355-356)
+ *   inv_std  = weights[..., top::s, left::s]   pts3d = xyz_noc[..., top::s, left::s] * noc_scale
+ *   pts2d    = gen_uv grid[top::s, left::s]    valid = ones                            (losses.py:142-161, 366)
+ *   loss_b   = Loss_cov_mixed(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d=..., max_err_len=...)   (losses.py:383)
+ * One launch produces loss (B) and the gradients w.r.t. xyz_noc (B,3,H,W), the logits (B,2,H,W) and weights_scale (B)
+ * (softmax backward included; un-sampled pixels get their exact gradient: 0 for xyz_noc, -w_j*S for the logits).
+ * fp32 only.  The (H,W) planes of xyz_noc / logits / their gradients must be contiguous (stride[3]==1, stride[2]==W).
+ */
+typedef struct lc_dense_args {
+    int32_t abi_version, B, H, W;
+    int32_t sample, top, left, reserved0;
+    double max_err_len, rel_thresh, w_e_thresh, grad_scale;
+    lc_view xyz_noc;       /* (B,3,H,W) */
+    lc_view logits;        /* (B,2,H,W) xyz_weight_logits */
+    lc_view weights_scale; /* (B) xyz_weights_scale */
+    lc_view noc_scale;     /* (B,3) */
+    lc_view K, pose, bbox; /* (B,3,3), (B,7), (B,8,3) */
+    lc_view grad_out;      /* (B) or NULL */
+    lc_view loss;          /* (B) */
+    lc_view g_xyz_noc;     /* (B,3,H,W) or NULL */
+    lc_view g_logits;      /* (B,2,H,W) or NULL */
+    lc_view g_scale;       /* (B) or NULL */
+    lc_view cov, update_cov; /* (B,6,6) or NULL */
+    int32_t* lc_flags;     /* (B) or NULL */
+    double* loss_sum;      /* (2) or NULL, see lc_args.loss_sum */
+} lc_dense_args;
+
+int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* cuda_stream);
+
 int lc_b200_abi_version(void);
 const char* lc_b200_last_error(void);
 

@@ -17,8 +17,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "liblc_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "csrc", "lc_pose.cuh"),
+           os.path.join(_HERE, "csrc", "lc_resident.cuh"),
            os.path.join(_ROOT, "include", "lc_b200.h")]
 BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 
@@ -29,7 +30,8 @@ FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN, FLAG_FORCE_STREAMIN
 ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
-           "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd")
+           "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd",
+           "lc_b200_dense_loss_fwd_bwd")
 
 
 class NativeLibraryError(RuntimeError):
@@ -57,6 +59,18 @@ class lc_args(C.Structure):
 
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+_DENSE_VIEWS = ("xyz_noc", "logits", "weights_scale", "noc_scale", "K", "pose", "bbox", "grad_out", "loss", "g_xyz_noc",
+                "g_logits", "g_scale", "cov", "update_cov")
+
+
+class lc_dense_args(C.Structure):
+    _fields_ = ([("abi_version", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                 ("sample", C.c_int32), ("top", C.c_int32), ("left", C.c_int32), ("reserved0", C.c_int32),
+                 ("max_err_len", C.c_double), ("rel_thresh", C.c_double), ("w_e_thresh", C.c_double), ("grad_scale", C.c_double)]
+                + [(f, lc_view) for f in _DENSE_VIEWS]
+                + [("lc_flags", C.c_void_p), ("loss_sum", C.c_void_p)])
 
 
 def nvcc_commands(out: str = LIB_PATH):
@@ -105,7 +119,8 @@ def lib() -> C.CDLL:
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name}")
         handle.lc_b200_last_error.restype = C.c_char_p
         for name in EXPORTS[3:]:
-            getattr(handle, name).argtypes = [C.POINTER(lc_args), C.c_void_p]
+            argt = lc_dense_args if name == "lc_b200_dense_loss_fwd_bwd" else lc_args
+            getattr(handle, name).argtypes = [C.POINTER(argt), C.c_void_p]
             getattr(handle, name).restype = C.c_int
         if handle.lc_b200_abi_version() != ABI_VERSION:
             raise NativeLibraryError("liblc_b200.so ABI version mismatch; rebuild")
@@ -188,7 +203,7 @@ def make_args(B: int, N: int, dtype: torch.dtype, **kw) -> lc_args:
     return a
 
 
-def call(name: str, args: lc_args, device: torch.device) -> int:
+def call(name: str, args, device: torch.device) -> int:
     """Enqueue one entry point on torch's current stream of `device`; returns the launch count."""
     handle = lib()
     with torch.cuda.device(device):

@@ -55,6 +55,23 @@ static int dispatch_jac(const lc_args* a, bool bwd, void* stream) {
     return check_launch(launch_stream_jac(*a, bwd, static_cast<cudaStream_t>(stream)));
 }
 
+static int dispatch_dense(const lc_dense_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->sample <= 0 || d->top < 0 || d->left < 0 || d->top >= d->H || d->left >= d->W)
+        return fail(LC_E_BADARG, "bad B / H / W / sample / top / left");
+    if (d->B == 0) return LC_OK;
+    if (!d->xyz_noc.ptr || !d->logits.ptr || !d->weights_scale.ptr || !d->noc_scale.ptr || !d->K.ptr || !d->pose.ptr || !d->bbox.ptr)
+        return fail(LC_E_NULL, "xyz_noc, logits, weights_scale, noc_scale, K, pose and bbox are required");
+    auto plane_ok = [&](const lc_view& v) { return !v.ptr || (v.stride[3] == 1 && v.stride[2] == d->W); };
+    if (!plane_ok(d->xyz_noc) || !plane_ok(d->logits) || !plane_ok(d->g_xyz_noc) || !plane_ok(d->g_logits))
+        return fail(LC_E_BADARG, "(H,W) planes must be contiguous");
+    const int rc = launch_dense(*d, static_cast<cudaStream_t>(stream));
+    if (rc == -1) return fail(LC_E_BADARG, "sampled point count does not fit in shared memory");
+    return check_launch(rc);
+}
+
 }  // namespace lc
 
 extern "C" {
@@ -68,5 +85,6 @@ int lc_b200_loss_fwd_bwd(const lc_args* a, void* stream) { return lc::dispatch_p
 int lc_b200_solve_loss(const lc_args* a, void* stream) { return lc::dispatch_pose(a, lc::MODE_LM | lc::MODE_LC, stream); }
 int lc_b200_pnp_jac_cov(const lc_args* a, void* stream) { return lc::dispatch_jac(a, false, stream); }
 int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatch_jac(a, true, stream); }
+int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* stream) { return lc::dispatch_dense(a, stream); }
 
 }  // extern "C"

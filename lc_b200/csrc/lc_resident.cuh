@@ -1,0 +1,348 @@
+// Building blocks of the shared-memory resident kernels (lc_resident.cu, lc_dense.cu): shared-memory layout,
+// asynchronous staging helpers (cp.async / TMA bulk + mbarrier), the fp64 LM evaluation pass and the LC phase.
+#pragma once
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "lc_pose.cuh"
+
+namespace lc {
+
+constexpr int kResidentMinN = 65;
+
+__host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
+
+struct ResLayout {
+    float *A0, *A1, *A2;  // X -> P
+    float *B0, *B1;       // x -> ec
+    float *S0, *S1;       // weights (raw staging only)
+};
+
+__device__ __forceinline__ ResLayout res_layout(unsigned char* base, int npad, bool raw) {
+    float* f = reinterpret_cast<float*>(base + ((sizeof(PoseShared) + 15) & ~size_t(15)));
+    ResLayout l;
+    l.A0 = f; l.A1 = f + npad; l.A2 = f + 2 * npad; l.B0 = f + 3 * npad; l.B1 = f + 4 * npad;
+    l.S0 = raw ? f + 5 * npad : nullptr;
+    l.S1 = raw ? f + 6 * npad : nullptr;
+    return l;
+}
+
+inline size_t resident_smem_bytes(int n, bool raw) {
+    return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * (raw ? 7 : 5) * static_cast<size_t>(round_up4(n));
+}
+
+__device__ __forceinline__ float ldf(const lc_view& v, int64_t off) { return static_cast<const float*>(v.ptr)[off]; }
+__device__ __forceinline__ void stf(const lc_view& v, int64_t off, float x) { static_cast<float*>(v.ptr)[off] = x; }
+__device__ __forceinline__ float nan_to_num_f(float x) {
+    if (isnan(x)) return 0.f;
+    if (isinf(x)) return x > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    return x;
+}
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register staging, every copy of a pose is in flight at once
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one instruction per contiguous slab ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
+
+// One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
+// staged fp32 arrays: cost, and when JAC also J'^T J' and J'^T r in the left basis.
+template <int NT, bool JAC>
+__device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
+    const LmState& L = s.lm;
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+    const double k00 = s.K[0], k01 = s.K[1], k10 = s.K[3], k11 = s.K[4], cx = s.K[2], cy = s.K[5];
+    const double R0 = L.Rm[0], R1 = L.Rm[1], R2 = L.Rm[2], R3 = L.Rm[3], R4 = L.Rm[4], R5 = L.Rm[5], R6 = L.Rm[6], R7 = L.Rm[7], R8 = L.Rm[8];
+    const double t0 = L.te[0], t1 = L.te[1], t2 = L.te[2];
+    // the sqrt-information weights are re-read from L2 every pass (8 B/point) instead of living in shared memory:
+    // that is what lets two CTAs share an SM at N = 4096.  The next point's weights are fetched before the
+    // current point is processed.
+    const float* pw = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
+    const int64_t swn = a.weights.stride[1], swc = a.weights.stride[2];
+    const bool icov = a.weight_mode == LC_W_ICOV_DIAG;
+    int i = threadIdx.x;
+    float w0 = 0.f, w1 = 0.f;
+    if (i < n) { w0 = pw[i * swn]; w1 = pw[i * swn + swc]; }
+    for (; i < n; i += NT) {
+        float wa = w0, wb = w1;
+        const int inext = i + NT;
+        if (inext < n) { w0 = pw[inext * swn]; w1 = pw[inext * swn + swc]; }
+        if (sanitize) { wa = nan_to_num_f(wa); wb = nan_to_num_f(wb); }
+        // cer_solver.py:37-38: L = diag(sqrt(icov)) in fp32.  For LC_W_INV_STD the reference's sqrt(fl(s*s)) is exactly
+        // |s| (barring overflow / underflow of s*s).
+        if (icov) { wa = sqrtf(wa); wb = sqrtf(wb); }
+        const double la = fabsf(wa), lc_ = fabsf(wb);
+        const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i];
+        const double px = l.B0[i], py = l.B1[i];
+        const double q0 = fma(R0, X0, fma(R1, X1, R2 * X2));
+        const double q1 = fma(R3, X0, fma(R4, X1, R5 * X2));
+        const double q2 = fma(R6, X0, fma(R7, X1, R8 * X2));
+        const double p0 = q0 + t0, p1 = q1 + t1, p2 = q2 + t2;
+        const double iz = fast_rcp(p2);
+        const double up = fma(p0, k00, p1 * k01) * iz, vp = fma(p0, k10, p1 * k11) * iz;
+        const double du = up - (px - cx), dv = vp - (py - cy);
+        const double r0 = du * la, r1 = dv * lc_;
+        acc[27] = fma(r0, r0, fma(r1, r1, acc[27]));
+        if (!JAC) continue;
+        const double a0 = la * iz, a1 = lc_ * iz;
+        double J0[6], J1[6];
+        J0[3] = a0 * k00; J0[4] = a0 * k01; J0[5] = -a0 * up;
+        J1[3] = a1 * k10; J1[4] = a1 * k11; J1[5] = -a1 * vp;
+        J0[0] = fma(q1, J0[5], -q2 * J0[4]); J0[1] = fma(q2, J0[3], -q0 * J0[5]); J0[2] = fma(q0, J0[4], -q1 * J0[3]);
+        J1[0] = fma(q1, J1[5], -q2 * J1[4]); J1[1] = fma(q2, J1[3], -q0 * J1[5]); J1[2] = fma(q0, J1[4], -q1 * J1[3]);
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = r; c < 6; ++c) {
+                acc[k] = fma(J0[r], J0[c], fma(J1[r], J1[c], acc[k]));
+                ++k;
+            }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc[21 + c] = fma(J0[c], r0, fma(J1[c], r1, acc[21 + c]));
+    }
+    acc[27] *= 0.5;
+    block_reduce<28, NT>(acc, s.red, s.fin);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LC phase on the staged arrays (A = X -> q, B = x -> ec), shared by the resident kernel and the dense-producer kernel
+// (lc_dense.cu).  WSrc supplies the inverse-std weights of point i, Sink receives the per-point gradients.
+// ---------------------------------------------------------------------------------------------
+struct DirectWeights {   // weights streamed from a strided (N,2) view (L2 resident after the first touch)
+    const float* p;
+    int64_t sn, sc;
+    __device__ __forceinline__ void get(int i, float& s0, float& s1) const { s0 = p[i * sn]; s1 = p[i * sn + sc]; }
+};
+struct DirectSink {      // gradients written to the strided views of lc_args
+    const lc_args& a;
+    int b;
+    __device__ __forceinline__ bool want_any() const { return a.g_pts3d.ptr || a.g_pts2d.ptr || a.g_weights.ptr; }
+    __device__ __forceinline__ bool want_pts3d() const { return a.g_pts3d.ptr != nullptr; }
+    __device__ __forceinline__ void weight_grad(int i, int c, float g, float) const {
+        if (a.g_weights.ptr) stf(a.g_weights, b * a.g_weights.stride[0] + i * a.g_weights.stride[1] + c * a.g_weights.stride[2], g);
+    }
+    __device__ __forceinline__ void pts2d_grad(int i, int c, float g) const {
+        if (a.g_pts2d.ptr) stf(a.g_pts2d, b * a.g_pts2d.stride[0] + i * a.g_pts2d.stride[1] + c * a.g_pts2d.stride[2], g);
+    }
+    __device__ __forceinline__ void pts3d_grad(int i, float g0, float g1, float g2) const {
+        const int64_t o = b * a.g_pts3d.stride[0] + i * a.g_pts3d.stride[1];
+        stf(a.g_pts3d, o, g0); stf(a.g_pts3d, o + a.g_pts3d.stride[2], g1); stf(a.g_pts3d, o + 2 * a.g_pts3d.stride[2], g2);
+    }
+};
+
+template <int NT, class WSrc, class Sink>
+__device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, const WSrc& wsrc, Sink& sink) {
+    const int tid = threadIdx.x;
+    if (tid == 0) lc_pose_setup(s, true);
+    __syncthreads();
+
+    const int64_t ovb = a.valid.ptr ? b * a.valid.stride[0] : 0;
+    // pass 1 (fp64): P = R X + t, project_apply + clamp_error once per point; P, ec kept as fp32 in place
+    {
+        const double Lmax = a.max_err_len;
+        const double lim = Lmax - 1e-6, lim2 = lim > 0.0 ? lim * lim : -1.0;   // |e|+1e-6 > Lmax  <=>  |e|^2 > lim2
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i], x0 = l.B0[i], x1 = l.B1[i];
+            const double q0 = fma(s.R[0], X0, fma(s.R[1], X1, s.R[2] * X2));
+            const double q1 = fma(s.R[3], X0, fma(s.R[4], X1, s.R[5] * X2));
+            const double q2 = fma(s.R[6], X0, fma(s.R[7], X1, s.R[8] * X2));
+            const double P0 = q0 + s.t[0], P1 = q1 + s.t[1], P2 = q2 + s.t[2];
+            const double KP0 = fma(s.K[0], P0, fma(s.K[1], P1, s.K[2] * P2));
+            const double KP1 = fma(s.K[3], P0, fma(s.K[4], P1, s.K[5] * P2));
+            const double KP2 = fma(s.K[6], P0, fma(s.K[7], P1, s.K[8] * P2));
+            const double iz = fast_rcp(KP2 > 0.1 ? KP2 : 0.1);
+            double e0 = fma(-KP0, iz, x0), e1 = fma(-KP1, iz, x1);
+            const double l2 = fma(e0, e0, e1 * e1);
+            if (l2 > lim2) {
+                const double len = sqrt(l2) + 1e-6;
+                const double f = (len - Lmax) / len;
+                e0 = fma(-f, e0, e0);
+                e1 = fma(-f, e1, e1);
+            }
+            const float ec0 = static_cast<float>(e0), ec1 = static_cast<float>(e1);
+            // q = R X is what is cached (not P = q + t): q x D then keeps fp32 relative precision even when |X| << |t|
+            l.A0[i] = static_cast<float>(q0); l.A1[i] = static_cast<float>(q1); l.A2[i] = static_cast<float>(q2);
+            l.B0[i] = ec0; l.B1[i] = ec1;
+            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
+            acc0 = fmaf(v, fabsf(ec0), acc0); acc1 = fmaf(v, fabsf(ec1), acc1); acc2 += v;
+        }
+        double acc[3] = {acc0, acc1, acc2};
+        block_reduce<3, NT>(acc, s.red, s.fin);
+    }
+    const double vcnt = a.valid.ptr ? s.fin[2] : static_cast<double>(n);
+    const float d0 = static_cast<float>(a.rel_thresh * (s.fin[0] / vcnt)), d1 = static_cast<float>(a.rel_thresh * (s.fin[1] / vcnt));
+    __syncthreads();
+    // pass 2 (fp32): q_a = mean valid s^2 sigma
+    {
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            float s0, s1;
+            wsrc.get(i, s0, s1);
+            const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
+            const float a0 = fabsf(l.B0[i]), a1 = fabsf(l.B1[i]);
+            const float sg0 = a0 > d0 ? d0 * (2.f * a0 - d0) : a0 * a0;
+            const float sg1 = a1 > d1 ? d1 * (2.f * a1 - d1) : a1 * a1;
+            acc0 = fmaf(v * (s0 * s0), sg0, acc0);
+            acc1 = fmaf(v * (s1 * s1), sg1, acc1);
+        }
+        double acc[2] = {acc0, acc1};
+        block_reduce<2, NT>(acc, s.red, s.fin);
+    }
+    // delta_k = sqrt(we * q_a / (sigma_k + 1e-6)) = sq_a * rsqrt(sigma_k + 1e-6)
+    const float sq0 = static_cast<float>(sqrt((s.fin[0] / vcnt) * a.w_e_thresh)), sq1 = static_cast<float>(sqrt((s.fin[1] / vcnt) * a.w_e_thresh));
+    __syncthreads();
+
+    const float t0 = static_cast<float>(s.t[0]), t1 = static_cast<float>(s.t[1]), t2 = static_cast<float>(s.t[2]);
+    const float k00 = static_cast<float>(s.K[0]), k01 = static_cast<float>(s.K[1]), k10 = static_cast<float>(s.K[3]), k11 = static_cast<float>(s.K[4]);
+    // Depth-decoupled accumulation basis.  For an object that is small compared to its depth every point has nearly
+    // the same normalised image position uv0, so the t_z Jacobian column D_z = -K uv0 / z is nearly a fixed combination
+    // of the t_x, t_y columns and H is ill conditioned (cond ~ (z/size)^2: the depth ambiguity).  The sums are therefore
+    // taken with the column t_z' = t_z + uc t_x + vc t_y, (uc, vc) = t_xy / t_z, whose entries
+    //   D_z + uc D_x + vc D_y = K (uvc - uv0) / z = K (uvc q_z - q_xy) / z^2
+    // are formed from the small vector q directly (no cancellation), and mapped back in fp64 (PoseShared::Tm).
+    const float uc = static_cast<float>(s.t[0] / s.t[2]), vc = static_cast<float>(s.t[1] / s.t[2]);
+
+    // per-point fp32 geometry shared by passes 3 and 4: left-basis Jacobian rows and robust weights
+    auto point_terms = [&](int i, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2], float (&w)[2]) {
+        const float q0 = l.A0[i], q1 = l.A1[i], q2 = l.A2[i];
+        const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
+        ec[0] = l.B0[i]; ec[1] = l.B1[i];
+        wsrc.get(i, sk[0], sk[1]);
+        const float iz = __fdividef(1.f, P2);
+        const float u0 = P0 * iz, v0 = P1 * iz;
+        const float du0 = fmaf(uc, q2, -q0) * iz, dv0 = fmaf(vc, q2, -q1) * iz;   // uvc - uv0
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float ka = c ? k10 : k00, kb = c ? k11 : k01;
+            const float e0 = ka * iz, e1 = kb * iz, e2 = -fmaf(ka, u0, kb * v0) * iz;
+            J[c][0] = fmaf(q1, e2, -q2 * e1);
+            J[c][1] = fmaf(q2, e0, -q0 * e2);
+            J[c][2] = fmaf(q0, e1, -q1 * e0);
+            J[c][3] = e0; J[c][4] = e1; J[c][5] = fmaf(ka, du0, kb * dv0) * iz;
+            const float dc = c ? d1 : d0, sq = c ? sq1 : sq0;
+            const float av = fabsf(ec[c]);
+            sg[c] = av > dc ? dc * (2.f * av - dc) : av * av;
+            del[c] = sq * rsqrtf(sg[c] + 1e-6f);
+            w[c] = sk[c] > del[c] ? del[c] * (2.f * sk[c] - del[c]) : sk[c] * sk[c];
+        }
+    };
+
+    // pass 3 (fp32 partial sums, fp64 CTA reduction): H' = sum W J'J'^T, G' = sum W^2 sigma J'J'^T, b' = sum W ec J'
+    {
+        float acc[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) acc[k] = 0.f;
+        for (int i = tid; i < n; i += NT) {
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, J, ec, sk, sg, del, w);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                acc_outer<0>(acc, w[c], J[c]);
+                acc_outer<21>(acc, w[c] * w[c] * sg[c], J[c]);
+                const float wb = w[c] * ec[c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[42 + r] = fmaf(wb, J[c][r], acc[42 + r]);
+            }
+        }
+        double accd[48];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) accd[k] = acc[k];
+        block_reduce<48, NT>(accd, s.red, s.fin);
+    }
+    lc_six_forward<float, NT>(a, s, b);
+    if (!sink.want_any()) return;
+    lc_six_backward<NT>(s);
+
+    // pass 4 (fp32): per-coordinate adjoints and the three input gradients
+    {
+        float cH[kSym], cG[kSym], bL[6];
+#pragma unroll
+        for (int k = 0; k < kSym; ++k) { cH[k] = static_cast<float>(s.cHL[k]); cG[k] = static_cast<float>(s.cGL[k]); }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bL[k] = static_cast<float>(s.bL[k]);
+        const float K0 = static_cast<float>(s.K[0]), K1 = static_cast<float>(s.K[1]), K2 = static_cast<float>(s.K[2]);
+        const float K3 = static_cast<float>(s.K[3]), K4 = static_cast<float>(s.K[4]), K5 = static_cast<float>(s.K[5]);
+        const float K6 = static_cast<float>(s.K[6]), K7 = static_cast<float>(s.K[7]), K8 = static_cast<float>(s.K[8]);
+        float Rf[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
+        for (int i = tid; i < n; i += NT) {
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, J, ec, sk, sg, del, w);
+            float ecb[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float qh = 0.f, qg = 0.f, lb = 0.f;
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    lb = fmaf(J[c][r], bL[r], lb);
+#pragma unroll
+                    for (int cc = r; cc < 6; ++cc) {
+                        const float pp = J[c][r] * J[c][cc];
+                        qh = fmaf(cH[k], pp, qh);
+                        qg = fmaf(cG[k], pp, qg);
+                        ++k;
+                    }
+                }
+                const float Wbar = qh + 2.f * w[c] * sg[c] * qg + ec[c] * lb;
+                const float sigbar = w[c] * w[c] * qg;
+                sink.weight_grad(i, c, Wbar * (sk[c] > del[c] ? 2.f * del[c] : 2.f * sk[c]), sk[c]);
+                const float dc = c ? d1 : d0;
+                const float av = fabsf(ec[c]);
+                const float sgn = (ec[c] > 0.f) ? 1.f : ((ec[c] < 0.f) ? -1.f : 0.f);
+                ecb[c] = sigbar * (av > dc ? 2.f * dc : 2.f * av) * sgn;
+                sink.pts2d_grad(i, c, ecb[c]);
+            }
+            if (sink.want_pts3d()) {
+                // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
+                const float P0 = l.A0[i] + t0, P1 = l.A1[i] + t1, P2 = l.A2[i] + t2;
+                const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
+                const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
+                const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
+                const bool act = KP2 >= 0.1f;
+                const float iz = __fdividef(1.f, act ? KP2 : 0.1f);
+                const float pr0 = act ? KP0 * iz : 0.f, pr1 = act ? KP1 * iz : 0.f;   // proj * [z >= 0.1]
+                const float gP0 = (fmaf(-pr0, K6, K0) * ecb[0] + fmaf(-pr1, K6, K3) * ecb[1]) * iz;
+                const float gP1 = (fmaf(-pr0, K7, K1) * ecb[0] + fmaf(-pr1, K7, K4) * ecb[1]) * iz;
+                const float gP2 = (fmaf(-pr0, K8, K2) * ecb[0] + fmaf(-pr1, K8, K5) * ecb[1]) * iz;
+                sink.pts3d_grad(i, -(Rf[0] * gP0 + Rf[3] * gP1 + Rf[6] * gP2), -(Rf[1] * gP0 + Rf[4] * gP1 + Rf[7] * gP2),
+                                -(Rf[2] * gP0 + Rf[5] * gP1 + Rf[8] * gP2));
+            }
+        }
+    }
+}
+
+}  // namespace lc

@@ -129,3 +129,36 @@ def p3(K, pts3d, pts2d, inv_std, bbox_3d, states, mode=3, max_iter=50, function_
                           _p(lcf, I), I(threads))
     return dict(states=st, radius=radius, invalid=invalid, iters=iters, loss=loss, g_pts3d=g3, g_pts2d=g2,
                 g_inv_std=gs, lc_flags=lcf)
+
+
+def dense_pose_loss(xyz_noc, logits, scale, noc_scale, K, pose, bbox_3d, sample, top_left, max_err_len=32.0):
+    """CPU restatement (numpy fp64 + lc_oracle.c) of the gdr-net glue of Loss_fn.dense_pose_loss and its backward:
+      losses.py:355-356  joint softmax over the 2*H*W logits, times xyz_weights_scale
+      losses.py:142-161  dense_pnp_matching_from_xyz: strided sub-sample of weights / xyz_noc*noc_scale / gen_uv grid
+      losses.py:366,383  valid = ones, Loss_cov_mixed(...)
+    Returns dict(loss (B,), g_xyz_noc (B,3,H,W), g_logits (B,2,H,W), g_scale (B,)) for d loss_b = 1.
+    Pinned by tests/golden/densex_*.npz (generated by the unmodified reference)."""
+    xyz_noc, logits = np.asarray(xyz_noc, np.float64), np.asarray(logits, np.float64)
+    scale = np.asarray(scale, np.float64).reshape(-1)
+    noc_scale = np.asarray(noc_scale, np.float64)
+    B, _, H, W = xyz_noc.shape
+    top, left = int(top_left[0]), int(top_left[1])
+    flat = logits.reshape(B, -1)
+    p = np.exp(flat - flat.max(1, keepdims=True))
+    p = (p / p.sum(1, keepdims=True)).reshape(B, 2, H, W)
+    w = p * scale[:, None, None, None]
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    sl = (slice(None), slice(None), slice(top, None, sample), slice(left, None, sample))
+    inv_std = w[sl].reshape(B, 2, -1).transpose(0, 2, 1)
+    pts3d = xyz_noc[sl].reshape(B, 3, -1).transpose(0, 2, 1) * noc_scale[:, None, :]
+    pts2d = np.stack((xs[top::sample, left::sample].reshape(-1), ys[top::sample, left::sample].reshape(-1)), -1)
+    pts2d = np.broadcast_to(pts2d, (B,) + pts2d.shape)
+    o = lc_loss(K, pose, pts3d, pts2d, inv_std, np.ones(pts3d.shape[:2]), bbox_3d, max_err_len=max_err_len)
+    Hn, Wn = len(range(top, H, sample)), len(range(left, W, sample))
+    g_w = np.zeros_like(w)
+    g_w[sl] = o["g_inv_std"].transpose(0, 2, 1).reshape(B, 2, Hn, Wn)
+    g_xyz = np.zeros_like(xyz_noc)
+    g_xyz[sl] = (o["g_pts3d"] * noc_scale[:, None, :]).transpose(0, 2, 1).reshape(B, 3, Hn, Wn)
+    S = (g_w * p).reshape(B, -1).sum(1)                       # d/d scale
+    g_logits = w * (g_w - S[:, None, None, None])             # softmax backward
+    return dict(loss=o["loss"], g_xyz_noc=g_xyz, g_logits=g_logits, g_scale=S)

@@ -107,9 +107,55 @@ def make_jac_exact():
     print("jacx_b3_n40:", os.path.getsize(path) // 1024, "KiB")
 
 
+def dense_inputs(B, H, W, seed):
+    """Network-output-shaped inputs whose back-projection roughly matches the pixel grid (plus noise/outliers)."""
+    g = torch.Generator().manual_seed(seed)
+    c = make_correspondences(B, 4, seed)
+    f64 = torch.float64
+    K, pose = c.K.clone(), c.pose
+    K[:, :2, :] = K[:, :2, :] * (W / 64.0)                       # crop of W x H pixels instead of 64 x 64
+    R = __import__("lc_b200.synth", fromlist=["quat_to_matrix"]).quat_to_matrix(pose[:, :4])
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=f64), torch.arange(W, dtype=f64), indexing="ij")
+    pix = torch.stack((xs, ys, torch.ones_like(xs)), -1).reshape(1, H * W, 3).expand(B, -1, -1)
+    z = pose[:, None, 6:7] + 40 * (2 * torch.rand(B, H * W, 1, generator=g, dtype=f64) - 1)
+    P = torch.linalg.solve(K, pix.mT).mT * z
+    X = (P - pose[:, None, 4:]) @ R                                # R^T (P - t)
+    noc_scale = torch.tensor([[40.0, 50.0, 60.0]], dtype=f64).expand(B, 3).clone()
+    X = X + 1.5 * torch.randn(B, H * W, 3, generator=g, dtype=f64)
+    xyz_noc = (X / noc_scale[:, None, :]).mT.reshape(B, 3, H, W)
+    logits = torch.randn(B, 2, H, W, generator=g, dtype=f64)
+    scale = (2.0 * H * W) * torch.exp(0.2 * torch.randn(B, 1, 1, 1, generator=g, dtype=f64))
+    r32 = lambda t: t.to(torch.float32).to(f64)
+    return dict(xyz_noc=r32(xyz_noc), logits=r32(logits), scale=r32(scale), noc_scale=r32(noc_scale), K=r32(K),
+                pose=r32(pose), bbox_3d=r32(c.bbox_3d))
+
+
+def make_dense():
+    """dense_pose_loss glue of the reference (losses.py:355-356, 142-161, 366, 383) run unmodified in fp64."""
+    import losses as ref_losses  # noqa: E402  (reference)
+    for name, B, H, W, sample, tl, seed in (("dense_b2_16x16_s2", 2, 16, 16, 2, (1, 0), 3), ("dense_b2_64x64_s2", 2, 64, 64, 2, (0, 1), 4),
+                                           ("dense_b2_40x56_s3", 2, 40, 56, 3, (2, 1), 5)):
+        d = dense_inputs(B, H, W, seed)
+        xyz = d["xyz_noc"].clone().requires_grad_(True)
+        lg = d["logits"].clone().requires_grad_(True)
+        sc = d["scale"].clone().requires_grad_(True)
+        w_raw = lg.reshape(lg.shape[:-3] + (1, -1)).softmax(dim=-1)
+        weights = w_raw.reshape_as(lg) * sc
+        p2, inv_std, p3, _ = ref_losses.dense_pnp_matching_from_xyz(xyz, weights, None, d["noc_scale"], sample=sample, top_left=tl)
+        valid = torch.ones_like(p3[..., 0])
+        loss = Loss_cov_mixed(d["K"], d["pose"], p3, p2, inv_std, valid, bbox_3d=d["bbox_3d"], max_err_len=32)
+        gx, gl, gs = torch.autograd.grad(loss.sum(), (xyz, lg, sc))
+        path = os.path.join(HERE, "densex_" + name[6:] + ".npz")
+        np.savez_compressed(path, **{("in_" + k): v.numpy().astype(np.float32) for k, v in d.items()},
+                            sample=np.array(sample), top_left=np.array(tl), ref_loss=loss.detach().numpy(),
+                            ref_g_xyz_noc=gx.numpy(), ref_g_logits=gl.numpy(), ref_g_scale=gs.numpy().reshape(B))
+        print(name, loss.detach().numpy(), os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     make_jac_exact()
+    make_dense()
     for name, B, N, seed, vmode, regime, store_jac in CASES:
         d = build_inputs(B, N, seed, vmode, regime)
         o = run_reference(d)

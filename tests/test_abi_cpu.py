@@ -20,7 +20,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     nat.build()
     handle = ctypes.CDLL(nat.LIB_PATH)
     declared = _declared_symbols()
-    assert len(declared) >= 8
+    assert len(declared) >= 9
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/lc_b200.h but not exported"
     assert set(declared) == set(nat.EXPORTS)
@@ -39,6 +39,19 @@ def test_struct_layout_matches_header(tmp_path):
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     A = nat.lc_args
     assert got == [ctypes.sizeof(A), A.K.offset, A.n_points.offset, A.loss.offset, A.invalid.offset, A.loss_sum.offset]
+
+
+def test_dense_struct_layout_matches_header(tmp_path):
+    c = tmp_path / "sz.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu",'
+                 'sizeof(lc_dense_args),offsetof(lc_dense_args,xyz_noc),offsetof(lc_dense_args,loss),'
+                 'offsetof(lc_dense_args,loss_sum));return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
+    exe = tmp_path / "sz"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([gcc, "-o", str(exe), str(c)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    A = nat.lc_dense_args
+    assert got == [ctypes.sizeof(A), A.xyz_noc.offset, A.loss.offset, A.loss_sum.offset]
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

@@ -106,3 +106,17 @@ def test_p3_driver_equals_separate_calls(oracle):
     lc = oracle.lc_loss(c.K.numpy(), lm["states"], c.pts3d.numpy(), c.pts2d.numpy(), c.inv_std.numpy(), None, c.bbox_3d.numpy())
     assert np.allclose(a["loss"], lc["loss"], rtol=1e-13)
     assert rel_err(a["g_pts3d"], lc["g_pts3d"]) < 1e-6   # p3 stores fp32 gradients
+
+
+@pytest.mark.parametrize("name", ["densex_b2_16x16_s2.npz", "densex_b2_64x64_s2.npz", "densex_b2_40x56_s3.npz"])
+def test_dense_producer_oracle_matches_reference_golden(oracle, name):
+    """oracle.dense_pose_loss == the reference's dense_pose_loss glue + Loss_cov_mixed + autograd (fp64)."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    o = oracle.dense_pose_loss(z["in_xyz_noc"], z["in_logits"], z["in_scale"], z["in_noc_scale"], z["in_K"], z["in_pose"],
+                               z["in_bbox_3d"], int(z["sample"]), tuple(z["top_left"]))
+    assert np.abs(o["loss"] - z["ref_loss"]).max() <= 1e-11 * np.abs(z["ref_loss"]).max()
+    assert rel_err(o["g_xyz_noc"], z["ref_g_xyz_noc"]) <= 1e-10
+    assert rel_err(o["g_logits"], z["ref_g_logits"]) <= 1e-10
+    assert np.abs(o["g_scale"] - z["ref_g_scale"]).max() <= 1e-10 * np.abs(z["ref_g_scale"]).max()
