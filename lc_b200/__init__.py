@@ -7,6 +7,7 @@ Public operators (same names and contracts as the reference modules they replace
     lc_b200.nll.pnp_auto.diff_pnp_perturb
     lc_b200.pnp.cer_solver.solve                     <- lib/pnp/cer_solver.py
     lc_b200.fused.solve_and_loss                     (solve -> loss -> grads in one launch)
+    lc_b200.dense.dense_pose_loss                    <- the glue of losses.py:355-386 fused with the loss (row f1)
     lc_b200.sharded.sharded_mean_loss                (batch-sharded mean with one scalar all-reduce)
 
 All of them call hand-written CUDA kernels through the C ABI in include/lc_b200.h.
