@@ -75,7 +75,7 @@ def solve(cam_mat: TensorOrList, pts3d: TensorOrList, pts2d: TensorOrList, icovs
     ``'solver_invalids'`` and ``'invalids'``.  ``num_workers`` is accepted and ignored (the batch is one
     launch); ``print_summary`` is ignored.
     """
-    dev = pts3d[0].device
+    dev = pts3d.device if isinstance(pts3d, Tensor) else pts3d[0].device
     if isinstance(pts3d, (list, tuple)):
         if n_points is None:
             n_points = [len(p) for p in pts3d]

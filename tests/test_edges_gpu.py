@@ -1,0 +1,91 @@
+"""GPU edge cases of the operator contracts: empty batches, sizes beyond the shared-memory resident limit (streaming
+fallback), the largest size a reference config produces (zycbv test: 128x128, dense_sample 1 -> N = 16384), un-batched
+and multi-dimensional leading shapes, non-contiguous K / pose, degenerate inputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import quat_angle, rel_err
+from lc_b200.synth import make_correspondences, planar_view
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_batch_is_a_noop_everywhere():
+    from lc_b200.cov_mixed import Loss_cov_mixed, loss_fwd_bwd
+    from lc_b200.pnp import cer_solver
+    from lc_b200.fused import solve_and_loss
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    o = loss_fwd_bwd(z(0, 3, 3), z(0, 7), z(0, 16, 3), z(0, 16, 2), z(0, 16, 2), None, z(0, 8, 3))
+    assert o["loss"].shape == (0,) and o["g_pts3d"].shape == (0, 16, 3)
+    p3 = z(0, 16, 3).requires_grad_(True)
+    l = Loss_cov_mixed(z(0, 3, 3), z(0, 7), p3, z(0, 16, 2), z(0, 16, 2), None, bbox_3d=z(0, 8, 3))
+    assert l.shape == (0,)
+    inv, st = cer_solver.solve(z(0, 3, 3), z(0, 16, 3), z(0, 16, 2), z(0, 16, 2), z(0, 7))
+    assert st.shape == (0, 7) and inv["invalids"].shape == (0,)
+    f = solve_and_loss(z(0, 3, 3), z(0, 7), z(0, 16, 3), z(0, 16, 2), z(0, 16, 2), None, z(0, 8, 3))
+    assert f["loss"].shape == (0,) and f["launches"] == 0
+
+
+@pytest.mark.parametrize("N", [12000, 16384])
+def test_sizes_beyond_the_resident_limit_take_the_streaming_kernel(oracle, N):
+    """N = 16384 is the largest size a reference config produces (configs/zycbv.yaml test: 128x128, dense_sample 1)."""
+    from lc_b200.fused import solve_and_loss
+    c = make_correspondences(2, N, 3).to(torch.float32)
+    ref = oracle.p3(c.K, c.pts3d, c.pts2d, c.inv_std, c.bbox_3d, c.start)
+    d = c.to(device="cuda")
+    o = solve_and_loss(d.K, d.start, planar_view(d.pts3d), d.pts2d, planar_view(d.inv_std), None, d.bbox_3d, need=(True, True, True))
+    assert np.array_equal(o["iters"].cpu().numpy(), ref["iters"]) and np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"])
+    st = o["states"].cpu().numpy().astype(np.float64)
+    assert quat_angle(st[:, :4], ref["states"][:, :4].astype(np.float64)).max() <= 1e-6
+    assert np.abs(o["loss"].cpu().numpy() - ref["loss"]).max() <= 1e-5 * np.abs(ref["loss"]).max()
+    for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
+        assert rel_err(o[k].cpu().numpy(), ref[k]) <= 1e-4, k
+
+
+def test_leading_shapes_and_noncontiguous_small_tensors(oracle):
+    """Reference operators take arbitrary leading dims (*,N,3); K may be an expanded (stride-0) tensor, pose a slice."""
+    from lc_b200.cov_mixed import Loss_cov_mixed
+    c = make_correspondences(6, 96, 4).to(torch.float32)
+    ref = oracle.lc_loss(c.K[:1].expand(6, 3, 3), c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
+    d = c.to(device="cuda")
+    pose_wide = torch.zeros(6, 9, device="cuda")
+    pose_wide[:, 1:8] = d.pose
+    loss = Loss_cov_mixed(d.K[:1].expand(2, 3, 3, 3), pose_wide[:, 1:8].reshape(2, 3, 7), d.pts3d.reshape(2, 3, 96, 3),
+                          d.pts2d.reshape(2, 3, 96, 2), d.inv_std.reshape(2, 3, 96, 2), None, bbox_3d=d.bbox_3d.reshape(2, 3, 8, 3))
+    assert loss.shape == (2, 3)
+    assert np.abs(loss.reshape(-1).cpu().numpy() - ref["loss"]).max() <= 2e-6 * np.abs(ref["loss"]).max()
+
+
+def test_degenerate_inputs_do_not_poison_the_batch():
+    """A sample with all-zero weights (non-SPD Hessian -> identity), one with NaN correspondences in the solver (flagged
+    invalid, start returned) and one with every point behind the z-clamp: the other samples are unaffected."""
+    from lc_b200.cov_mixed import loss_fwd_bwd
+    from lc_b200.pnp import cer_solver
+    c = make_correspondences(4, 128, 8).to(torch.float32).to(device="cuda")
+    base = loss_fwd_bwd(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
+    s = c.inv_std.clone(); s[1] = 0
+    X = c.pts3d.clone(); X[2] = X[2] - 1e5 * torch.tensor([0, 0, 1.0], device="cuda")      # far behind the camera
+    o = loss_fwd_bwd(c.K, c.pose, X, c.pts2d, s, None, c.bbox_3d)
+    assert torch.isfinite(o["loss"][[0, 1, 3]]).all()
+    assert torch.equal(o["loss"][[0, 3]], base["loss"][[0, 3]]) and torch.equal(o["g_pts3d"][[0, 3]], base["g_pts3d"][[0, 3]])
+    x = c.pts2d.clone(); x[0, :, :] = float("nan")
+    inv, st = cer_solver.solve(c.K, c.pts3d, x, c.inv_std ** 2, c.start)
+    assert inv["invalids"].cpu().tolist() == [True, False, False, False]
+    assert torch.equal(st[0], c.start[0]) and torch.isfinite(st[1:]).all()
+
+
+def test_fp64_tensors_through_the_python_operators(oracle):
+    from lc_b200.cov_mixed import Loss_cov_mixed
+    from lc_b200.pnp import cer_solver
+    c = make_correspondences(3, 300, 12)
+    ref = oracle.lc_loss(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
+    d = c.to(device="cuda")
+    p3 = d.pts3d.clone().requires_grad_(True)
+    loss = Loss_cov_mixed(d.K, d.pose, p3, d.pts2d, d.inv_std, None, bbox_3d=d.bbox_3d)
+    assert loss.dtype == torch.float64
+    loss.sum().backward()
+    assert np.abs(loss.detach().cpu().numpy() - ref["loss"]).max() <= 1e-9 * np.abs(ref["loss"]).max()
+    assert rel_err(p3.grad.cpu().numpy(), ref["g_pts3d"]) <= 1e-9
+    inv, st = cer_solver.solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start)
+    assert st.dtype == torch.float64 and not inv["invalids"].any()
