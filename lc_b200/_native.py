@@ -141,12 +141,12 @@ def view_of(t: Optional[torch.Tensor]) -> lc_view:
     if t is None:
         v.ptr = None
         return v
-    v.ptr = t.data_ptr()
     st = t.stride()
-    if len(st) > 4:
+    n = len(st)
+    if n > 4:
         raise ValueError("lc_view supports at most 4 dimensions")
-    for i, s in enumerate(st):
-        v.stride[i] = s
+    v.ptr = t.data_ptr()
+    v.stride[:n] = st
     return v
 
 
@@ -178,6 +178,18 @@ def empty_like_dense(t: torch.Tensor) -> torch.Tensor:
     return torch.empty_like(t)
 
 
+def fit(t: Optional[torch.Tensor], shape: tuple, dtype: torch.dtype) -> Optional[torch.Tensor]:
+    """t as `dtype` broadcast to `shape`; returns t itself when nothing has to change (the common case: this is
+    on the per-call critical path of small batches)."""
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if tuple(t.shape) != shape:
+        t = t.expand(shape)
+    return t
+
+
 def make_args(B: int, N: int, dtype: torch.dtype, **kw) -> lc_args:
     """Fill an lc_args; tensor-valued keywords become views, int/float keywords are copied."""
     a = lc_args()
@@ -203,12 +215,19 @@ def make_args(B: int, N: int, dtype: torch.dtype, **kw) -> lc_args:
     return a
 
 
+def as_c_float(x: float) -> float:
+    """x rounded to a C float and back: the reference ABI carries function_tolerance as `float` (ext.h:10)."""
+    return C.c_float(x).value
+
+
 def call(name: str, args, device: torch.device) -> int:
     """Enqueue one entry point on torch's current stream of `device`; returns the launch count."""
     handle = lib()
-    with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
-        rc = getattr(handle, name)(C.byref(args), C.c_void_p(stream))
+    if torch.cuda.current_device() == device.index:
+        rc = getattr(handle, name)(C.byref(args), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    else:
+        with torch.cuda.device(device):
+            rc = getattr(handle, name)(C.byref(args), C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {handle.lc_b200_last_error().decode()}")
     return handle.lc_b200_last_launch_count()

@@ -36,16 +36,10 @@ def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std:
     dev = nat.check_cuda(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, grad_out)
     dt = pts3d.dtype
     B, N = pts3d.shape[0], pts3d.shape[1]
-    K, pose, pts2d, inv_std, bbox_3d = (t.to(dt) for t in (K, pose, pts2d, inv_std, bbox_3d))
-    K = K.expand(B, 3, 3)
-    pose = pose.expand(B, 7)
-    bbox_3d = bbox_3d.expand(B, 8, 3)
-    pts2d = pts2d.expand(B, N, 2)
-    inv_std = inv_std.expand(B, N, 2)
-    if valid is not None:
-        valid = valid.to(dt).expand(B, N)
-    if grad_out is not None:
-        grad_out = grad_out.to(dt).expand(B)
+    fit = nat.fit
+    K, pose, bbox_3d = fit(K, (B, 3, 3), dt), fit(pose, (B, 7), dt), fit(bbox_3d, (B, 8, 3), dt)
+    pts2d, inv_std = fit(pts2d, (B, N, 2), dt), fit(inv_std, (B, N, 2), dt)
+    valid, grad_out = fit(valid, (B, N), dt), fit(grad_out, (B,), dt)
     loss = torch.empty(B, dtype=dt, device=dev)
     flags = torch.empty(B, dtype=torch.int32, device=dev)
     dense_like = nat.empty_like_dense

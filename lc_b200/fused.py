@@ -27,19 +27,23 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
     dt = pts3d.dtype
     B, N = pts3d.shape[:2]
     o = out or {}
-    new = lambda key, *shape, dtype=dt: o[key] if key in o else torch.empty(*shape, dtype=dtype, device=dev)
+    if not all(k in o for k in ("states", "radius", "loss", "invalid", "iters", "flags")):
+        # two allocations instead of six: the small per-pose outputs are views of one float and one int32 buffer
+        fbuf = torch.empty(9 * B, dtype=dt, device=dev)
+        ibuf = torch.empty(3 * B, dtype=torch.int32, device=dev)
+        o = dict(o, states=fbuf[: 7 * B].view(B, 7), radius=fbuf[7 * B: 8 * B], loss=fbuf[8 * B:],
+                 invalid=ibuf[:B], iters=ibuf[B: 2 * B], flags=ibuf[2 * B:])
     dense_like = lambda key, t: o[key] if key in o else nat.empty_like_dense(t)
-    res = dict(states=new("states", B, 7), radius=new("radius", B), invalid=new("invalid", B, dtype=torch.int32),
-               iters=new("iters", B, dtype=torch.int32), loss=new("loss", B), flags=new("flags", B, dtype=torch.int32),
+    res = dict(states=o["states"], radius=o["radius"], invalid=o["invalid"], iters=o["iters"], loss=o["loss"], flags=o["flags"],
                g_pts3d=dense_like("g_pts3d", pts3d) if need[0] else None,
                g_pts2d=dense_like("g_pts2d", pts2d.expand(B, N, 2)) if need[1] else None,
                g_inv_std=dense_like("g_inv_std", inv_std) if need[2] else None)
     flags = (nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0) | (nat.FLAG_FORCE_STREAMING if force_streaming else 0)
-    ftol = float(torch.tensor(function_tolerance, dtype=torch.float32))
-    args = nat.make_args(B, N, dt, K=K.to(dt).expand(B, 3, 3), pose=start.to(dt).expand(B, 7), pts3d=pts3d,
-                         pts2d=pts2d.to(dt).expand(B, N, 2), weights=inv_std.to(dt),
-                         valid=None if valid is None else valid.to(dt).expand(B, N), bbox=bbox_3d.to(dt).expand(B, 8, 3),
-                         grad_out=None if grad_out is None else grad_out.to(dt).expand(B),
+    ftol = nat.as_c_float(function_tolerance)
+    fit = nat.fit
+    args = nat.make_args(B, N, dt, K=fit(K, (B, 3, 3), dt), pose=fit(start, (B, 7), dt), pts3d=pts3d,
+                         pts2d=fit(pts2d, (B, N, 2), dt), weights=fit(inv_std, (B, N, 2), dt),
+                         valid=fit(valid, (B, N), dt), bbox=fit(bbox_3d, (B, 8, 3), dt), grad_out=fit(grad_out, (B,), dt),
                          loss=res["loss"], g_pts3d=res["g_pts3d"], g_pts2d=res["g_pts2d"], g_weights=res["g_inv_std"],
                          state=res["states"], radius=res["radius"], invalid=res["invalid"], iters=res["iters"],
                          lc_flags=res["flags"], flags=flags, weight_mode=nat.W_INV_STD, max_iter=int(max_iter_count),

@@ -52,10 +52,11 @@ def lm_solve(cam_mat: Tensor, pts3d: Tensor, pts2d: Tensor, weights: Tensor, sta
     flags = ((nat.FLAG_NAN_TO_NUM if filter_input_nan else 0) | (nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0)
              | (nat.FLAG_FORCE_STREAMING if force_streaming else 0))
     # the reference ABI carries function_tolerance as a C float (ext.h:10)
-    ftol = float(torch.tensor(function_tolerance, dtype=torch.float32))
+    ftol = nat.as_c_float(function_tolerance)
     npts = None if n_points is None else n_points.to(device=dev, dtype=torch.int32).contiguous()
-    args = nat.make_args(B, N, dt, K=cam_mat.to(dt).expand(B, 3, 3), pose=start.to(dt).expand(B, 7), pts3d=pts3d,
-                         pts2d=pts2d.to(dt).expand(B, N, 2), weights=weights.to(dt), n_points=npts, state=state,
+    fit = nat.fit
+    args = nat.make_args(B, N, dt, K=fit(cam_mat, (B, 3, 3), dt), pose=fit(start, (B, 7), dt), pts3d=pts3d,
+                         pts2d=fit(pts2d, (B, N, 2), dt), weights=weights if weights.dtype == dt else weights.to(dt), n_points=npts, state=state,
                          radius=radius, invalid=invalid, iters=iters, trace=trace, flags=flags,
                          weight_mode=int(weight_mode), max_iter=int(max_iter_count), function_tolerance=ftol)
     nat.call("lc_b200_lm_solve", args, dev)
