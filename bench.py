@@ -257,16 +257,26 @@ def main():
         return d["pts3d"].transpose(1, 2), d["pts2d"].transpose(1, 2), d["inv_std"].transpose(1, 2)
 
     outs = {}
-    # [sum of losses, count] accumulators the kernel adds into; a small ring so consecutive steps do not alias
-    sums = torch.zeros(8, 2, dtype=torch.float64, device=dev)
+    # [sum of losses, count] accumulators the kernel adds into.  The 16-byte all-reduce of step i runs on a side stream
+    # so that it overlaps the kernel of step i+1 (nothing on the data path depends on it: every rank scales its own
+    # gradients by 1/B_global); a ring of slots + events keeps a slot from being re-zeroed before its reduce is done.
+    RING = 8
+    sums = torch.zeros(RING, 2, dtype=torch.float64, device=dev)
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    ev_kernel = [torch.cuda.Event() for _ in range(RING)]
+    ev_reduced = [torch.cuda.Event() for _ in range(RING)]
     counter = [0]
 
     def step(d, out):
         p3, p2, s = views(d)
-        acc = None
+        acc, k = None, 0
+        main = torch.cuda.current_stream(dev)
         if world > 1 and a.pipeline != "p2":
-            acc = sums[counter[0] % 8]
+            k = counter[0] % RING
+            if counter[0] >= RING:
+                main.wait_event(ev_reduced[k])
             counter[0] += 1
+            acc = sums[k]
             acc.zero_()
         if a.pipeline == "p3":
             r = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, out=out, loss_sum=acc)
@@ -274,8 +284,14 @@ def main():
             r = loss_fwd_bwd(d["K"], d["pose"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, loss_sum=acc)
         else:
             r = lm_solve(d["K"], p3, p2, s, d["start"], weight_mode=nat.W_INV_STD)
-        # the path's only exchange: one 16-byte all-reduce of [sum of losses, count] (losses.py:334,386 take the mean)
-        m = global_mean_from_sums(acc) if acc is not None else None
+        m = None
+        if acc is not None:
+            # the path's only exchange: one 16-byte all-reduce of [sum of losses, count] (losses.py:334,386 take the mean)
+            ev_kernel[k].record(main)
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev_kernel[k])
+                m = global_mean_from_sums(acc)
+                ev_reduced[k].record(comm_stream)
         return r, m
 
     def barrier():
