@@ -24,6 +24,10 @@ struct DenseGeom {
 };
 
 // inv_std of sampled point i = softmax(logits)[pix] * scale, recomputed from the logits (L1/L2 resident)
+// exp() of a non-positive logit difference: ex2.approx via __expf (2 instructions, ~1e-6 relative) — the same function
+// is used for the normaliser, the weights and the epilogue, so the softmax stays exactly normalised to itself.
+__device__ __forceinline__ float sm_exp(float x) { return __expf(x); }
+
 struct SoftmaxWeights {
     const float* l0;   // logits plane a = 0 of this sample
     const float* l1;   // plane a = 1
@@ -31,8 +35,8 @@ struct SoftmaxWeights {
     float m, k;        // max logit, scale / sum exp
     __device__ __forceinline__ void get(int i, float& s0, float& s1) const {
         const int p = g.pix(i);
-        s0 = expf(l0[p] - m) * k;
-        s1 = expf(l1[p] - m) * k;
+        s0 = sm_exp(l0[p] - m) * k;
+        s1 = sm_exp(l1[p] - m) * k;
     }
 };
 
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(NT, 2) lc_dense_kernel(const lc_dense_args d, 
     double se[1] = {0.0};
     {
         float acc = 0.f;
-        for (int j = tid; j < 2 * HW; j += NT) acc += expf(lg[(j >= HW ? lgc : 0) + (j >= HW ? j - HW : j)] - m);
+        for (int j = tid; j < 2 * HW; j += NT) acc += sm_exp(lg[(j >= HW ? lgc : 0) + (j >= HW ? j - HW : j)] - m);
         se[0] = acc;
     }
     block_reduce<1, NT>(se, s.red, s.fin);
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(NT, 2) lc_dense_kernel(const lc_dense_args d, 
         const bool sampled = dy >= 0 && dx >= 0 && (dy % d.sample) == 0 && (dx % d.sample) == 0;
         const int i = sampled ? (dy / d.sample) * g.Wn + dx / d.sample : 0;
         if (gl) {
-            const float w0 = expf(lg[p] - m) * kk, w1 = expf(lg[lgc + p] - m) * kk;
+            const float w0 = sm_exp(lg[p] - m) * kk, w1 = sm_exp(lg[lgc + p] - m) * kk;
             gl[p] = w0 * ((sampled ? l.B0[i] : 0.f) - S);
             gl[glc + p] = w1 * ((sampled ? l.B1[i] : 0.f) - S);
         }
@@ -162,11 +166,13 @@ __global__ void __launch_bounds__(NT, 2) lc_dense_kernel(const lc_dense_args d, 
 template <int NT>
 static int launch_dense_t(const lc_dense_args& d, const lc_args& a, int n, int max_smem, cudaStream_t st) {
     const size_t smem = resident_smem_bytes(n, false);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
         const cudaError_t e = cudaFuncSetAttribute(lc_dense_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured = true;
+        configured[dev] = true;
     }
     lc_dense_kernel<NT><<<d.B, NT, smem, st>>>(d, a, round_up4(n));
     return static_cast<int>(cudaGetLastError());

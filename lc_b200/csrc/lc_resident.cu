@@ -168,11 +168,13 @@ static int tma_mask_for(const lc_args& a) {
 template <int NT, int MODE>
 static int launch_res_t(const lc_args& a, cudaStream_t st) {
     const size_t smem = resident_smem_bytes(a.N, false);
-    static size_t configured = 0;   // per instantiation
-    if (smem > configured) {
-        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_optin_smem()));
+    static bool configured[64] = {};   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured = static_cast<size_t>(max_optin_smem());
+        configured[dev] = true;
     }
     lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(a.N), tma_mask_for(a));
     return static_cast<int>(cudaGetLastError());
