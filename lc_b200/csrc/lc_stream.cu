@@ -178,7 +178,7 @@ __device__ __forceinline__ void lm_eval_pass(const lc_args& a, PoseShared& s, in
 // the fused per-pose kernel (streaming)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NT, int MODE>
-__global__ void __launch_bounds__(NT) lc_pose_kernel(const lc_args a) {
+__global__ void __launch_bounds__(NT, (NT <= 64) ? (1024 / NT / 2) : 1) lc_pose_kernel(const lc_args a) {
     __shared__ PoseShared s;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
