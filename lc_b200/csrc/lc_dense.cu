@@ -75,7 +75,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 2) lc_dense_kernel(const lc_dense_args d, const lc_args a, int npad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
-    const ResLayout l = res_layout(smem_raw, npad, false);
+    const ResLayout l = res_layout(smem_raw, npad);
     const int b = blockIdx.x, tid = threadIdx.x;
     DenseGeom g;
     g.H = d.H; g.W = d.W; g.sample = d.sample; g.top = d.top; g.left = d.left;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NT, 2) lc_dense_kernel(const lc_dense_args d, 
 
 template <int NT>
 static int launch_dense_t(const lc_dense_args& d, const lc_args& a, int n, int max_smem, cudaStream_t st) {
-    const size_t smem = resident_smem_bytes(n, false);
+    const size_t smem = resident_smem_bytes(n);
     static bool configured[64] = {};   // per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -186,7 +186,7 @@ int launch_dense(const lc_dense_args& d, cudaStream_t st) {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
         return static_cast<int>(cudaGetLastError());
     }
-    if (resident_smem_bytes(n, false) > static_cast<size_t>(max_smem)) return -1;
+    if (resident_smem_bytes(n) > static_cast<size_t>(max_smem)) return -1;
     // the LC phase reads its scalars and outputs through an lc_args
     lc_args a{};
     a.abi_version = LC_B200_ABI_VERSION; a.B = d.B; a.N = n; a.dtype = LC_F32;

@@ -17,7 +17,7 @@ struct LmState {
     double x[6], xc[6];        // accepted point / candidate, [angle-axis, t]
     double A[kSym], gs[6];     // scaled J^T J (packed) and scaled gradient at x
     double scale[6], diag[6];
-    double cost, cost_c, radius, dec, xnorm, gmax, model_change, reported_radius;
+    double cost, radius, dec, xnorm, gmax, model_change, reported_radius;
     double Rm[9], Jl[9], te[3];  // rotation, left Jacobian and translation of the evaluation point
     int reuse_diag, n_invalid, it, step_ok, any_success, ctl, term, pad;
 };

@@ -26,9 +26,8 @@ namespace lc {
 template <int NT, int MODE>
 __global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr bool RAW = false;   // weights are never staged: they are streamed from L2 (see lm_eval_pass_res)
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
-    const ResLayout l = res_layout(smem_raw, npad, RAW);
+    const ResLayout l = res_layout(smem_raw, npad);
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
@@ -145,7 +144,7 @@ static int max_optin_smem() {
 bool resident_supported(const lc_args& a, int mode) {
     if (a.dtype != LC_F32 || a.N < kResidentMinN) return false;
     if ((mode & MODE_LM) && a.weight_mode != LC_W_ICOV_DIAG && a.weight_mode != LC_W_INV_STD) return false;
-    const size_t need = resident_smem_bytes(a.N, false);
+    const size_t need = resident_smem_bytes(a.N);
     return need <= static_cast<size_t>(max_optin_smem());
 }
 
@@ -167,7 +166,7 @@ static int tma_mask_for(const lc_args& a) {
 
 template <int NT, int MODE>
 static int launch_res_t(const lc_args& a, cudaStream_t st) {
-    const size_t smem = resident_smem_bytes(a.N, false);
+    const size_t smem = resident_smem_bytes(a.N);
     static bool configured[64] = {};   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
     int dev = 0;
     cudaGetDevice(&dev);

@@ -13,23 +13,21 @@ constexpr int kResidentMinN = 65;
 
 __host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
 
+// planar fp32 arrays behind the PoseShared block (20 B/point)
 struct ResLayout {
-    float *A0, *A1, *A2;  // X -> P
-    float *B0, *B1;       // x -> ec
-    float *S0, *S1;       // weights (raw staging only)
+    float *A0, *A1, *A2;  // X, later q = R X
+    float *B0, *B1;       // x, later the clamped error ec
 };
 
-__device__ __forceinline__ ResLayout res_layout(unsigned char* base, int npad, bool raw) {
+__device__ __forceinline__ ResLayout res_layout(unsigned char* base, int npad) {
     float* f = reinterpret_cast<float*>(base + ((sizeof(PoseShared) + 15) & ~size_t(15)));
     ResLayout l;
     l.A0 = f; l.A1 = f + npad; l.A2 = f + 2 * npad; l.B0 = f + 3 * npad; l.B1 = f + 4 * npad;
-    l.S0 = raw ? f + 5 * npad : nullptr;
-    l.S1 = raw ? f + 6 * npad : nullptr;
     return l;
 }
 
-inline size_t resident_smem_bytes(int n, bool raw) {
-    return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * (raw ? 7 : 5) * static_cast<size_t>(round_up4(n));
+inline size_t resident_smem_bytes(int n) {
+    return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * 5 * static_cast<size_t>(round_up4(n));
 }
 
 __device__ __forceinline__ float ldf(const lc_view& v, int64_t off) { return static_cast<const float*>(v.ptr)[off]; }

@@ -124,3 +124,23 @@ def full_icov_from_inv_std(inv_std: torch.Tensor, seed: int) -> torch.Tensor:
     c, s = torch.cos(th), torch.sin(th)
     Rm = torch.stack((c, -s, s, c), -1).reshape(inv_std.shape[:-1] + (2, 2))
     return Rm @ torch.diag_embed(inv_std ** 2) @ Rm.mT
+
+
+def make_dense_outputs(B: int, H: int, W: int, seed: int):
+    """Network-output-shaped tensors for the dense path (``losses.py:336-386``): ``xyz_noc (B,3,H,W)`` whose
+    back-projection roughly matches the pixel grid (plus noise), weight logits ``(B,2,H,W)``, ``xyz_weights_scale
+    (B,1,1,1)``, ``noc_scale (B,3)`` and K / pose / bbox_3d.  fp32 on the CPU."""
+    g = torch.Generator().manual_seed(int(seed))
+    c = make_correspondences(B, 4, seed)
+    K = c.K.clone()
+    K[:, :2, :] *= W / 64.0                                  # crop of W pixels instead of 64
+    R = quat_to_matrix(c.pose[:, :4])
+    f64 = torch.float64
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=f64), torch.arange(W, dtype=f64), indexing="ij")
+    pix = torch.stack((xs, ys, torch.ones_like(xs)), -1).reshape(1, H * W, 3).expand(B, -1, -1)
+    zc = c.pose[:, None, 6:7] + 40 * (2 * torch.rand(B, H * W, 1, generator=g, dtype=f64) - 1)
+    X = (torch.linalg.solve(K, pix.mT).mT * zc - c.pose[:, None, 4:]) @ R + torch.randn(B, H * W, 3, generator=g, dtype=f64)
+    ns = torch.tensor([[40.0, 50.0, 60.0]], dtype=f64).expand(B, 3)
+    return dict(xyz_noc=(X / ns[:, None, :]).mT.reshape(B, 3, H, W).float(), logits=torch.randn(B, 2, H, W, generator=g),
+                scale=(2.0 * H * W) * torch.exp(0.2 * torch.randn(B, 1, 1, 1, generator=g)), noc_scale=ns.float(), K=K.float(),
+                pose=c.pose.float(), bbox_3d=c.bbox_3d.float())

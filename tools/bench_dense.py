@@ -3,11 +3,10 @@
 Config C1 of SURVEY.md §8 (glmo train: B=32, 64x64 head, dense_sample=2 -> N=1024) and larger batches."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 from lc_b200.dense import dense_loss_fwd_bwd
 from lc_b200.cov_mixed import Loss_cov_mixed
-from test_dense_gpu import _inputs
+from lc_b200.synth import make_dense_outputs as _inputs
 
 def timeit(fn, reps):
     for _ in range(5): fn()
