@@ -111,23 +111,23 @@ __device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s
         const double du = up - (px - cx), dv = vp - (py - cy);
         const double r0 = du * la, r1 = dv * lc_;
         acc[27] = fma(r0, r0, fma(r1, r1, acc[27]));
-        // one Jacobian row at a time (6 live values instead of 12: the kernel runs at the 128-register cap)
-#pragma unroll
-        for (int row = 0; row < (JAC ? 2 : 0); ++row) {
-            const double aw = (row ? lc_ : la) * iz, rr = row ? r1 : r0;
-            double J[6];
-            J[3] = aw * (row ? k10 : k00); J[4] = aw * (row ? k11 : k01); J[5] = -aw * (row ? vp : up);
-            J[0] = fma(q1, J[5], -q2 * J[4]); J[1] = fma(q2, J[3], -q0 * J[5]); J[2] = fma(q0, J[4], -q1 * J[3]);
+        if (JAC) {
+            const double a0 = la * iz, a1 = lc_ * iz;
+            double J0[6], J1[6];
+            J0[3] = a0 * k00; J0[4] = a0 * k01; J0[5] = -a0 * up;
+            J1[3] = a1 * k10; J1[4] = a1 * k11; J1[5] = -a1 * vp;
+            J0[0] = fma(q1, J0[5], -q2 * J0[4]); J0[1] = fma(q2, J0[3], -q0 * J0[5]); J0[2] = fma(q0, J0[4], -q1 * J0[3]);
+            J1[0] = fma(q1, J1[5], -q2 * J1[4]); J1[1] = fma(q2, J1[3], -q0 * J1[5]); J1[2] = fma(q0, J1[4], -q1 * J1[3]);
             int k = 0;
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int c = r; c < 6; ++c) {
-                    acc[k] = fma(J[r], J[c], acc[k]);
+                    acc[k] = fma(J0[r], J0[c], fma(J1[r], J1[c], acc[k]));
                     ++k;
                 }
 #pragma unroll
-            for (int c = 0; c < 6; ++c) acc[21 + c] = fma(J[c], rr, acc[21 + c]);
+            for (int c = 0; c < 6; ++c) acc[21 + c] = fma(J0[c], r0, fma(J1[c], r1, acc[21 + c]));
         }
     }
     acc[27] *= 0.5;
