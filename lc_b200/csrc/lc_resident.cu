@@ -148,9 +148,11 @@ bool resident_supported(const lc_args& a, int mode) {
     return need <= static_cast<size_t>(max_optin_smem());
 }
 
-static int resident_threads_for(int n) {
+// 128 threads (4 CTAs/SM) while a thread still gets >= 8 points per pass, 256 threads (2 CTAs/SM) above; measured on
+// B200: the loss phase prefers the finer granularity up to N ~ 1.3k, the solver alone up to N ~ 512.
+static int resident_threads_for(int n, int mode) {
     if (const char* e = getenv("LC_B200_RES_NT")) return atoi(e);   // tuning knob for benchmarks
-    return n <= 512 ? 128 : 256;
+    return n <= ((mode & MODE_LC) ? 1280 : 512) ? 128 : 256;
 }
 
 // A (B,N,C) fp32 view can be staged by 1-D TMA bulk copies when every component slab is contiguous (point stride 1)
@@ -183,7 +185,7 @@ template <int MODE>
 static int launch_res_m(const lc_args& a, cudaStream_t st) {
     // 256 threads x 2 CTAs per SM (20 B/point of shared memory): one CTA's 6x6 / trust-region sections and loads
     // overlap the other CTA's point passes
-    if (resident_threads_for(a.N) == 128) return launch_res_t<128, MODE>(a, st);
+    if (resident_threads_for(a.N, MODE) == 128) return launch_res_t<128, MODE>(a, st);
     return launch_res_t<256, MODE>(a, st);
 }
 

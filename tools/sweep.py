@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--max-bytes", type=float, default=6e9)
     ap.add_argument("--points", default="8,1024,4096")
     ap.add_argument("--bmax", type=int, default=65536)
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle port (all host cores) once per N on a bounded sample")
     a = ap.parse_args()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
@@ -42,8 +43,23 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
-    rows = []
+    rows, cpu_rows = [], []
     for n in [int(x) for x in a.points.split(",")]:
+        if a.cpu:
+            import time
+            from oracle import cpu_oracle
+            cores = os.cpu_count() or 1
+            sample = max(8, min(4096 if n <= 64 else 256, 16 * cores if n <= 1024 else 4 * cores))
+            c = make_correspondences(sample, n, 7).to(torch.float32)
+            for pipe, mode, st in (("p1", 2, c.pose), ("p2", 1, c.start), ("p3", 3, c.start)):
+                arrs = [t.numpy() for t in (c.K, c.pts3d, c.pts2d, c.inv_std, c.bbox_3d, st)]
+                cpu_oracle.p3(*arrs, mode=mode, threads=cores)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    cpu_oracle.p3(*arrs, mode=mode, threads=cores)
+                dt = (time.perf_counter() - t0) / 3
+                cpu_rows.append((n, pipe, sample, cores, sample / dt))
+                print(f"N={n:5d} CPU port {pipe}: {sample / dt:12.0f} poses/s ({cores} cores, sample {sample})", flush=True)
         B = 1
         while B <= a.bmax:
             in_bytes = B * n * 28
@@ -91,6 +107,11 @@ def main():
             f.write("| N | B | pipeline | us/launch | poses/s | algorithmic GB/s | % of HBM peak |\n|---|---|---|---|---|---|---|\n")
             for r in rows:
                 f.write(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]:.1f} | {r[4]:.0f} | {r[5]:.1f} | {100 * r[6]:.1f} |\n")
+            if cpu_rows:
+                f.write("\n## CPU oracle port on the box's host cores (OpenMP over poses; a baseline, not a target)\n\n")
+                f.write("| N | pipeline | sample poses | cores | poses/s |\n|---|---|---|---|---|\n")
+                for r in cpu_rows:
+                    f.write(f"| {r[0]} | {r[1]} | {r[2]} | {r[3]} | {r[4]:.0f} |\n")
 
 
 if __name__ == "__main__":
