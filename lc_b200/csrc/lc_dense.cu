@@ -72,7 +72,7 @@ __device__ __forceinline__ float block_max(float v, double* red, double* fin) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 2) lc_dense_kernel(const lc_dense_args d, const lc_args a, int npad) {
+__global__ void __launch_bounds__(NT, 512 / NT) lc_dense_kernel(const lc_dense_args d, const lc_args a, int npad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
     const ResLayout l = res_layout(smem_raw, npad);
@@ -193,7 +193,7 @@ int launch_dense(const lc_dense_args& d, cudaStream_t st) {
     a.max_err_len = d.max_err_len; a.rel_thresh = d.rel_thresh; a.w_e_thresh = d.w_e_thresh; a.grad_scale = d.grad_scale;
     a.K = d.K; a.pose = d.pose; a.bbox = d.bbox; a.grad_out = d.grad_out; a.loss = d.loss; a.cov = d.cov; a.update_cov = d.update_cov;
     a.lc_flags = d.lc_flags; a.loss_sum = d.loss_sum;
-    return n <= 1280 ? launch_dense_t<128>(d, a, n, max_smem, st) : launch_dense_t<256>(d, a, n, max_smem, st);
+    return n <= 2048 ? launch_dense_t<128>(d, a, n, max_smem, st) : launch_dense_t<256>(d, a, n, max_smem, st);
 }
 
 }  // namespace lc

@@ -24,7 +24,7 @@
 namespace lc {
 
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
+__global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
     const ResLayout l = res_layout(smem_raw, npad);
@@ -148,11 +148,13 @@ bool resident_supported(const lc_args& a, int mode) {
     return need <= static_cast<size_t>(max_optin_smem());
 }
 
-// 128 threads (4 CTAs/SM) while a thread still gets >= 8 points per pass, 256 threads (2 CTAs/SM) above; measured on
-// B200: the loss phase prefers the finer granularity up to N ~ 1.3k, the solver alone up to N ~ 512.
-static int resident_threads_for(int n, int mode) {
+// 128 threads x 4 CTAs per SM while four poses fit in shared memory (N <= 2048: 40 KB + 15 KB each), 256 threads x 2
+// CTAs above.  Both give 16 warps/SM at 128 registers; the finer granularity hides the per-pose serial sections
+// better (measured on B200 at equal total points: N = 1024 P3 511 vs 651 us, N = 2048 389 vs 442 us; N = 2900, where
+// only three 128-thread CTAs fit, prefers 256).
+static int resident_threads_for(int n, int) {
     if (const char* e = getenv("LC_B200_RES_NT")) return atoi(e);   // tuning knob for benchmarks
-    return n <= ((mode & MODE_LC) ? 1280 : 512) ? 128 : 256;
+    return n <= 2048 ? 128 : 256;
 }
 
 // A (B,N,C) fp32 view can be staged by 1-D TMA bulk copies when every component slab is contiguous (point stride 1)
