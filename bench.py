@@ -46,7 +46,7 @@ def algorithmic_bytes_per_pose(pipeline: str, n: int) -> int:
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pipeline", default="p3", choices=["p3", "p1", "p2"])
@@ -88,7 +88,7 @@ def run_cpu_port(pipeline: str, n_pts: int, sample: int, steps: int, warmup: int
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons sampled every ~5 ms through NVML (nvidia_ml_py) during the timed region;
+    """SM clock + throttle reasons sampled every ~1 ms through NVML (nvidia_ml_py) during the timed region;
     falls back to `nvidia-smi -lms 20` if NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -109,7 +109,7 @@ class ClockSampler:
                 self.samples.append((sm, reasons))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.001)
 
     def start(self):
         try:
