@@ -22,6 +22,9 @@
  *   lc_b200_pnp_jac_cov     weighted_pnp_jac_wrt_pts2d(...,      lib/nll/pnp_auto.py:111-135
  *                           with_cov=True) forward
  *   lc_b200_pnp_jac_cov_bwd its double-backward w.r.t. weights   lib/nll/pnp_auto.py:129-134
+ *   lc_b200_dense_loss_fwd_bwd  the producer glue of Loss_fn.dense_pose_loss fused in front of the loss
+ *                           (gdr-net and zebrapose branches)     losses.py:336-386, 142-184, floatbits.py:49-160
+ *   lc_b200_noc_bin_decode  nn_out_to_xyz(..., inference=True)   losses.py:16-45, floatbits.py:33-47, 197-224
  *
  * Layout: every array is described by an lc_view = base pointer + strides IN ELEMENTS, so the
  * planar (B,N,C) views the dense call site produces (strides (C*N,1,N), losses.py:142-161),
@@ -37,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LC_B200_ABI_VERSION 1
+#define LC_B200_ABI_VERSION 2
 
 enum { LC_F32 = 0, LC_F64 = 1 };
 
@@ -142,9 +145,42 @@ typedef struct lc_dense_args {
     lc_view cov, update_cov; /* (B,6,6) or NULL */
     int32_t* lc_flags;     /* (B) or NULL */
     double* loss_sum;      /* (2) or NULL, see lc_args.loss_sum */
+
+    /*
+     * ZebraPose producer ("next" row f3).  When noc_bin_logits.ptr != NULL, pts3d comes from the Gray-coded bit logits
+     * instead of xyz_noc (which is then ignored, as is g_xyz_noc): the zebrapose branch of dense_pose_loss,
+     *   dense_pnp_matching_from_noc_bin                      losses.py:163-184
+     *   nn_out_to_xyz(raw_bits_gt=..., noc_mask=..., ...)   losses.py:16-45   (noc * noc_scale, model transform)
+     *   floatbits.nn_logits2noc_with_gt                      floatbits.py:49-69, 99-160 (MSB-error soft decoding)
+     * and its backward: per sampled in-mask pixel and axis exactly one bit channel receives a gradient.
+     */
+    lc_view noc_bin_logits;  /* (B,C,H,W) fp32, C = bit_cnt[0]+bit_cnt[1]+bit_cnt[2], contiguous (H,W) planes */
+    lc_view noc_bin_raw;     /* (B,C,H,W) uint8 / bool ground-truth raw bits, any strides (nn_noc2target returns channel-last storage) */
+    lc_view msk_noc;         /* (B,H,W) uint8 / bool, any strides */
+    lc_view model_transform; /* (B,4,4) fp32 or NULL: xyz = (xyz_xformed - T[:3,3]) @ T[:3,:3] */
+    lc_view g_noc_bin;       /* (B,C,H,W) fp32 or NULL, contiguous (H,W) planes */
+    int32_t bit_cnt[3];      /* bits per axis (floatbits.calc_bit_count), 1..16 each */
+    int32_t black_background; /* floatbits._black_background: the two leading bits of every axis are stored inverted */
 } lc_dense_args;
 
 int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* cuda_stream);
+
+/*
+ * Test-time ZebraPose decode (row f3): nn_out_to_xyz(nn_out, noc_scale, model_transform=..., bit_cnt=..., inference=True)
+ * (losses.py:16-45) = floatbits.nn_logits2noc without LUT (floatbits.py:33-47, 197-224: hard Gray bits -> binary, soft LSB),
+ * times noc_scale, model transform.  One pass: reads C*4 bytes and writes 12 bytes per pixel.
+ */
+typedef struct lc_decode_args {
+    int32_t abi_version, B, H, W;
+    int32_t bit_cnt[3];
+    int32_t black_background;
+    lc_view noc_bin_logits;  /* (B,C,H,W) fp32, contiguous (H,W) planes */
+    lc_view noc_scale;       /* (B,3) */
+    lc_view model_transform; /* (B,4,4) or NULL */
+    lc_view xyz;             /* out (B,H,W,3) fp32, any strides: [batch, row, col, component] */
+} lc_decode_args;
+
+int lc_b200_noc_bin_decode(const lc_decode_args* a, void* cuda_stream);
 
 int lc_b200_abi_version(void);
 const char* lc_b200_last_error(void);

@@ -23,7 +23,7 @@ HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "cs
            os.path.join(_ROOT, "include", "lc_b200.h")]
 BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LC_F32, LC_F64 = 0, 1
 W_ICOV_DIAG, W_ICOV_FULL, W_INV_STD, W_SQRT_L = 0, 1, 2, 3
 FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN, FLAG_FORCE_STREAMING = 1, 2, 4, 8
@@ -31,7 +31,7 @@ ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
            "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd",
-           "lc_b200_dense_loss_fwd_bwd")
+           "lc_b200_dense_loss_fwd_bwd", "lc_b200_noc_bin_decode")
 
 
 class NativeLibraryError(RuntimeError):
@@ -65,12 +65,23 @@ _DENSE_VIEWS = ("xyz_noc", "logits", "weights_scale", "noc_scale", "K", "pose", 
                 "g_logits", "g_scale", "cov", "update_cov")
 
 
+_ZEBRA_VIEWS = ("noc_bin_logits", "noc_bin_raw", "msk_noc", "model_transform", "g_noc_bin")
+
+
 class lc_dense_args(C.Structure):
     _fields_ = ([("abi_version", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                  ("sample", C.c_int32), ("top", C.c_int32), ("left", C.c_int32), ("reserved0", C.c_int32),
                  ("max_err_len", C.c_double), ("rel_thresh", C.c_double), ("w_e_thresh", C.c_double), ("grad_scale", C.c_double)]
                 + [(f, lc_view) for f in _DENSE_VIEWS]
-                + [("lc_flags", C.c_void_p), ("loss_sum", C.c_void_p)])
+                + [("lc_flags", C.c_void_p), ("loss_sum", C.c_void_p)]
+                + [(f, lc_view) for f in _ZEBRA_VIEWS]
+                + [("bit_cnt", C.c_int32 * 3), ("black_background", C.c_int32)])
+
+
+class lc_decode_args(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("bit_cnt", C.c_int32 * 3), ("black_background", C.c_int32),
+                ("noc_bin_logits", lc_view), ("noc_scale", lc_view), ("model_transform", lc_view), ("xyz", lc_view)]
 
 
 def nvcc_commands(out: str = LIB_PATH):
@@ -119,7 +130,7 @@ def lib() -> C.CDLL:
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name}")
         handle.lc_b200_last_error.restype = C.c_char_p
         for name in EXPORTS[3:]:
-            argt = lc_dense_args if name == "lc_b200_dense_loss_fwd_bwd" else lc_args
+            argt = {"lc_b200_dense_loss_fwd_bwd": lc_dense_args, "lc_b200_noc_bin_decode": lc_decode_args}.get(name, lc_args)
             getattr(handle, name).argtypes = [C.POINTER(argt), C.c_void_p]
             getattr(handle, name).restype = C.c_int
         if handle.lc_b200_abi_version() != ABI_VERSION:

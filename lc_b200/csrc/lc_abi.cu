@@ -74,14 +74,34 @@ static int dispatch_dense(const lc_dense_args* d, void* stream) {
     if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->sample <= 0 || d->top < 0 || d->left < 0 || d->top >= d->H || d->left >= d->W)
         return fail(LC_E_BADARG, "bad B / H / W / sample / top / left");
     if (d->B == 0) return LC_OK;
-    if (!d->xyz_noc.ptr || !d->logits.ptr || !d->weights_scale.ptr || !d->noc_scale.ptr || !d->K.ptr || !d->pose.ptr || !d->bbox.ptr)
-        return fail(LC_E_NULL, "xyz_noc, logits, weights_scale, noc_scale, K, pose and bbox are required");
+    const bool zebra = d->noc_bin_logits.ptr != nullptr;
+    if (!(zebra || d->xyz_noc.ptr) || !d->logits.ptr || !d->weights_scale.ptr || !d->noc_scale.ptr || !d->K.ptr || !d->pose.ptr || !d->bbox.ptr)
+        return fail(LC_E_NULL, "xyz_noc (or noc_bin_logits), logits, weights_scale, noc_scale, K, pose and bbox are required");
     auto plane_ok = [&](const lc_view& v) { return !v.ptr || (v.stride[3] == 1 && v.stride[2] == d->W); };
-    if (!plane_ok(d->xyz_noc) || !plane_ok(d->logits) || !plane_ok(d->g_xyz_noc) || !plane_ok(d->g_logits))
+    if (!plane_ok(d->xyz_noc) || !plane_ok(d->logits) || !plane_ok(d->g_xyz_noc) || !plane_ok(d->g_logits) ||
+        !plane_ok(d->noc_bin_logits) || !plane_ok(d->g_noc_bin))
         return fail(LC_E_BADARG, "(H,W) planes must be contiguous");
+    if (zebra) {
+        if (!d->noc_bin_raw.ptr || !d->msk_noc.ptr) return fail(LC_E_NULL, "noc_bin_raw and msk_noc are required with noc_bin_logits");
+        for (int k = 0; k < 3; ++k)
+            if (d->bit_cnt[k] < 1 || d->bit_cnt[k] > 16) return fail(LC_E_BADARG, "bit_cnt entries must be in 1..16");
+    }
     const int rc = launch_dense(*d, static_cast<cudaStream_t>(stream));
     if (rc == -1) return fail(LC_E_BADARG, "sampled point count does not fit in shared memory");
     return check_launch(rc);
+}
+
+static int dispatch_decode(const lc_decode_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->H <= 0 || d->W <= 0) return fail(LC_E_BADARG, "bad B / H / W");
+    for (int k = 0; k < 3; ++k)
+        if (d->bit_cnt[k] < 1 || d->bit_cnt[k] > 16) return fail(LC_E_BADARG, "bit_cnt entries must be in 1..16");
+    if (d->B == 0) return LC_OK;
+    if (!d->noc_bin_logits.ptr || !d->noc_scale.ptr || !d->xyz.ptr) return fail(LC_E_NULL, "noc_bin_logits, noc_scale and xyz are required");
+    if (d->noc_bin_logits.stride[3] != 1 || d->noc_bin_logits.stride[2] != d->W) return fail(LC_E_BADARG, "(H,W) planes must be contiguous");
+    return check_launch(launch_decode(*d, static_cast<cudaStream_t>(stream)));
 }
 
 }  // namespace lc
@@ -98,5 +118,6 @@ int lc_b200_solve_loss(const lc_args* a, void* stream) { return lc::dispatch_pos
 int lc_b200_pnp_jac_cov(const lc_args* a, void* stream) { return lc::dispatch_jac(a, false, stream); }
 int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatch_jac(a, true, stream); }
 int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* stream) { return lc::dispatch_dense(a, stream); }
+int lc_b200_noc_bin_decode(const lc_decode_args* a, void* stream) { return lc::dispatch_decode(a, stream); }
 
 }  // extern "C"

@@ -535,5 +535,6 @@ int launch_stream_jac(const lc_args& a, bool bwd, cudaStream_t st);
 bool resident_supported(const lc_args& a, int mode);
 int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st);
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
+int launch_decode(const lc_decode_args& d, cudaStream_t st);
 
 }  // namespace lc

@@ -144,3 +144,52 @@ def make_dense_outputs(B: int, H: int, W: int, seed: int):
     return dict(xyz_noc=(X / ns[:, None, :]).mT.reshape(B, 3, H, W).float(), logits=torch.randn(B, 2, H, W, generator=g),
                 scale=(2.0 * H * W) * torch.exp(0.2 * torch.randn(B, 1, 1, 1, generator=g)), noc_scale=ns.float(), K=K.float(),
                 pose=c.pose.float(), bbox_3d=c.bbox_3d.float())
+
+
+def make_zebra_outputs(B: int, H: int, W: int, seed: int, bit_cnt=(7, 6, 5), *, with_transform: bool = True,
+                       flip_prob: float = 0.08, mask_prob: float = 0.8, black_background: bool = True):
+    """ZebraPose-shaped network outputs for the dense path (``losses.py:163-184``): Gray-coded bit logits
+    ``bin_logits (B,sum(bit_cnt),H,W)`` that mostly agree with the ground-truth code of a surface consistent with the
+    pose (a fraction ``flip_prob`` of the bits is wrong), the GT raw bits ``raw_bits`` (bool, channel-last storage like
+    ``floatbits.nn_noc2target`` returns), ``msk_noc (B,H,W)`` bool, a model transform ``(B,4,4)`` and the tensors of
+    ``make_dense_outputs``.  The bit coding restates ``floatbits.py:76-97``."""
+    d = make_dense_outputs(B, H, W, seed)
+    g = torch.Generator().manual_seed(int(seed) + 4242)
+    f64 = torch.float64
+    ns = d["noc_scale"].to(f64)
+    X = (d["xyz_noc"].to(f64) * ns[:, :, None, None]).permute(0, 2, 3, 1)          # (B,H,W,3) model frame
+    if with_transform:
+        q = torch.randn(B, 4, generator=g, dtype=f64)
+        M = quat_to_matrix(q)
+        tt = 3.0 * torch.randn(B, 3, generator=g, dtype=f64)
+        T = torch.eye(4, dtype=f64).repeat(B, 1, 1)
+        T[:, :3, :3], T[:, :3, 3] = M, tt
+        Xf = X @ M.mT[:, None] + tt[:, None, None, :]                              # losses.py:56 xyz @ T[:3,:3]^T + T[:3,3]
+        ns_x = Xf.abs().amax(dim=(1, 2)) * 1.02
+    else:
+        T, Xf, ns_x = None, X, ns * 1.5
+    noc = (Xf / ns_x[:, None, None, :]).clamp(-0.999, 0.999)
+    bit_cnt = [int(b) for b in bit_cnt]
+    mods, raws = [], []
+    for a, N in enumerate(bit_cnt):
+        mx = 2 ** N - 1
+        ints = torch.clamp((noc[..., a] + 1) * (mx * 0.5), 0, mx).round().to(torch.int64)
+        raw = ((ints[..., None] >> torch.arange(N - 1, -1, -1)) & 1).bool()
+        mod = raw.clone()
+        mod[..., 1:] ^= raw[..., :-1]
+        if black_background:
+            mod[..., 0:2] = ~mod[..., 0:2]
+        mods.append(mod)
+        raws.append(raw)
+    mod, raw = torch.cat(mods, -1), torch.cat(raws, -1)                             # (B,H,W,C)
+    mag = 0.2 + 2.5 * torch.rand(mod.shape, generator=g, dtype=f64)
+    # wrong bits are rarer towards the MSB (a half-trained network gets the coarse code right first)
+    pos = torch.cat([torch.arange(1, N + 1, dtype=f64) / N for N in bit_cnt])
+    flip = torch.rand(mod.shape, generator=g, dtype=f64) < flip_prob * pos * pos
+    logits = (mod ^ flip).to(f64).mul(2).sub(1) * mag
+    msk = torch.rand(B, H, W, generator=g) < mask_prob
+    out = dict(d)
+    out.pop("xyz_noc")
+    out.update(bin_logits=logits.permute(0, 3, 1, 2).contiguous().float(), raw_bits=raw.permute(0, 3, 1, 2), msk_noc=msk,
+               noc_scale=ns_x.float(), model_transform=None if T is None else T.float(), bit_cnt=bit_cnt)
+    return out

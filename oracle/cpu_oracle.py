@@ -162,3 +162,148 @@ def dense_pose_loss(xyz_noc, logits, scale, noc_scale, K, pose, bbox_3d, sample,
     S = (g_w * p).reshape(B, -1).sum(1)                       # d/d scale
     g_logits = w * (g_w - S[:, None, None, None])             # softmax backward
     return dict(loss=o["loss"], g_xyz_noc=g_xyz, g_logits=g_logits, g_scale=S)
+
+
+# ------------------------------------------------------------------------------------------------
+# ZebraPose binary-code producer
+# ------------------------------------------------------------------------------------------------
+def _axis_slices(bit_cnt):
+    bit_cnt = [int(b) for b in ([bit_cnt] * 3 if np.isscalar(bit_cnt) else bit_cnt)]
+    off = np.concatenate(([0], np.cumsum(bit_cnt)))
+    return bit_cnt, [slice(int(off[a]), int(off[a + 1])) for a in range(3)]
+
+
+def noc_to_bits(noc, bit_cnt, black_background=True):
+    """floatbits.py:76-97 mod_noc2bits_bb / :13-31 nn_noc2target: noc (B,H,W,3) in (-1,1) -> (mod_bits, raw_bits), both
+    (B,sum(bit_cnt),H,W) bool.  raw = MSB-first binary of round(clamp((noc+1)*max/2, 0, max)); mod = Gray code of it with
+    the two leading bits inverted under a black background."""
+    noc = np.asarray(noc, np.float64)
+    bit_cnt, _ = _axis_slices(bit_cnt)
+    mods, raws = [], []
+    for a, N in enumerate(bit_cnt):
+        mx = 2 ** N - 1
+        ints = np.rint(np.clip((noc[..., a] + 1) * (mx * 0.5), 0, mx)).astype(np.int64)   # torch.round = half-to-even = rint
+        raw = ((ints[..., None] >> np.arange(N - 1, -1, -1)) & 1).astype(bool)
+        mod = raw.copy()
+        mod[..., 1:] ^= raw[..., :-1]
+        if black_background:
+            mod[..., 0:2] = ~mod[..., 0:2]
+        mods.append(mod)
+        raws.append(raw)
+    return np.concatenate(mods, -1).transpose(0, 3, 1, 2), np.concatenate(raws, -1).transpose(0, 3, 1, 2)
+
+
+def noc_bin_decode_with_gt(logits, raw_bits, msk, bit_cnt, black_background=True):
+    """floatbits.py:49-69 nn_logits2noc_with_gt -> :99-160 mod_logits2float_with_gt_bb_scripted, per axis:
+      signed logits l' = l * m, m_j = -1 where the previous GT bit is set, m_0, m_1 *= -1 (black background)   (:139-142)
+      pred = l' > 0; idx = first bit where pred != gt (the LSB if none)                                          (:146-152)
+      in-mask value  = sum of GT bits except bit idx, weighted 2^(N-1-j), + sigmoid(l'_idx) * 2^(N-1-idx)       (:153-157)
+      out-mask value = sum of pred bits weighted                                                                (:147)
+      noc = val / (max_val/2) - 1                                                                               (:112)
+    logits (B,C,H,W) float, raw_bits (B,C,H,W) bool, msk (B,H,W) bool.
+    Returns noc (B,H,W,3) and, for the backward, sel (B,H,W,3) channel index carrying the gradient and
+    dnoc (B,H,W,3) = d noc_a / d logits[sel_a] (0 outside the mask)."""
+    logits = np.asarray(logits, np.float64)
+    raw_bits = np.asarray(raw_bits).astype(bool)
+    msk = np.asarray(msk).astype(bool)
+    bit_cnt, sls = _axis_slices(bit_cnt)
+    B, _, H, W = logits.shape
+    noc = np.zeros((B, H, W, 3))
+    sel = np.zeros((B, H, W, 3), np.int64)
+    dnoc = np.zeros((B, H, W, 3))
+    bf = -1.0 if black_background else 1.0
+    for a, (N, sl) in enumerate(zip(bit_cnt, sls)):
+        l = logits[:, sl].transpose(0, 2, 3, 1)
+        g = raw_bits[:, sl].transpose(0, 2, 3, 1)
+        m = np.ones_like(l)
+        m[..., 1:][g[..., :-1]] = -1.0
+        m[..., 0:2] *= bf
+        lp = l * m
+        wgt = 2.0 ** np.arange(N - 1, -1, -1)
+        pred = lp > 0
+        out_val = (pred * wgt).sum(-1)
+        err = pred ^ g
+        err[..., -1] = True
+        idx = np.argmax(err, -1)
+        g_wo = g.copy()
+        np.put_along_axis(g_wo, idx[..., None], False, -1)
+        lsel = np.take_along_axis(lp, idx[..., None], -1)[..., 0]
+        sg = 1.0 / (1.0 + np.exp(-lsel))
+        in_val = (g_wo * wgt).sum(-1) + sg * wgt[idx]
+        val = np.where(msk, in_val, out_val)
+        half = (2 ** N - 1) * 0.5
+        noc[..., a] = val / half - 1
+        sel[..., a] = sl.start + idx
+        dnoc[..., a] = np.where(msk, sg * (1 - sg) * wgt[idx] * np.take_along_axis(m, idx[..., None], -1)[..., 0] / half, 0.0)
+    return noc, sel, dnoc
+
+
+def noc_bin_decode(logits, bit_cnt, black_background=True):
+    """floatbits.py:33-47 nn_logits2noc (inference, no LUT) -> :197-224 mod_logits2float_bb, per axis: hard Gray bits
+    (leading two inverted under a black background) -> binary integer; its LSB is replaced by
+    sigmoid(l_last * (1 - (val & 2))).  Returns noc (B,H,W,3)."""
+    logits = np.asarray(logits, np.float64)
+    bit_cnt, sls = _axis_slices(bit_cnt)
+    B, _, H, W = logits.shape
+    noc = np.zeros((B, H, W, 3))
+    for a, (N, sl) in enumerate(zip(bit_cnt, sls)):
+        l = logits[:, sl].transpose(0, 2, 3, 1)
+        bits = l > 0
+        if black_background:
+            bits[..., 0:2] = ~bits[..., 0:2]
+        binb = np.bitwise_xor.accumulate(bits.astype(np.int64), axis=-1)     # Gray -> binary, MSB first
+        val = (binb * (2 ** np.arange(N - 1, -1, -1))).sum(-1)
+        lsb_factor = 1 - (val & 2)
+        v = (val & -2) + 1.0 / (1.0 + np.exp(-(l[..., -1] * lsb_factor)))
+        noc[..., a] = v / ((2 ** N - 1) * 0.5) - 1
+    return noc
+
+
+def dense_pose_loss_noc_bin(bin_logits, raw_bits, msk_noc, logits, scale, noc_scale, K, pose, bbox_3d, bit_cnt, sample,
+                            top_left, model_transform=None, max_err_len=32.0, black_background=True):
+    """CPU restatement of the ZebraPose branch of Loss_fn.dense_pose_loss and its backward:
+      losses.py:355-356  joint softmax * scale (as dense_pose_loss above)
+      losses.py:163-184  dense_pnp_matching_from_noc_bin: strided sub-sample, nn_out_to_xyz(raw_bits_gt, noc_mask, ...)
+      losses.py:16-45    nn_out_to_xyz: noc * noc_scale, then (xyz - T[:3,3]) @ T[:3,:3] with the model transform
+      losses.py:375,383  valid = ones, Loss_cov_mixed(...)
+    Returns dict(loss, g_bin_logits (B,C,H,W), g_logits (B,2,H,W), g_scale (B,), pts3d (B,n,3))."""
+    logits = np.asarray(logits, np.float64)
+    scale = np.asarray(scale, np.float64).reshape(-1)
+    noc_scale = np.asarray(noc_scale, np.float64)
+    B, C_, H, W = np.asarray(bin_logits).shape
+    top, left = int(top_left[0]), int(top_left[1])
+    flat = logits.reshape(B, -1)
+    p = np.exp(flat - flat.max(1, keepdims=True))
+    p = (p / p.sum(1, keepdims=True)).reshape(B, 2, H, W)
+    w = p * scale[:, None, None, None]
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing="ij")
+    sl = (slice(None), slice(None), slice(top, None, sample), slice(left, None, sample))
+    sl3 = (slice(None), slice(top, None, sample), slice(left, None, sample))
+    inv_std = w[sl].reshape(B, 2, -1).transpose(0, 2, 1)
+    noc, sel, dnoc = noc_bin_decode_with_gt(np.asarray(bin_logits)[sl], np.asarray(raw_bits)[sl], np.asarray(msk_noc)[sl3],
+                                            bit_cnt, black_background)
+    Hn, Wn = noc.shape[1], noc.shape[2]
+    xf = noc * noc_scale[:, None, None, :]
+    if model_transform is not None:
+        T = np.asarray(model_transform, np.float64)
+        M = T[:, :3, :3]
+        xyz = np.einsum("bhwa,bak->bhwk", xf - T[:, None, None, :3, 3], M)
+    else:
+        M = np.broadcast_to(np.eye(3), (B, 3, 3))
+        xyz = xf
+    pts3d = xyz.reshape(B, -1, 3)
+    pts2d = np.stack((xs[top::sample, left::sample].reshape(-1), ys[top::sample, left::sample].reshape(-1)), -1)
+    pts2d = np.broadcast_to(pts2d, (B,) + pts2d.shape)
+    o = lc_loss(K, pose, pts3d, pts2d, inv_std, np.ones(pts3d.shape[:2]), bbox_3d, max_err_len=max_err_len)
+    g_w = np.zeros_like(w)
+    g_w[sl] = o["g_inv_std"].transpose(0, 2, 1).reshape(B, 2, Hn, Wn)
+    S = (g_w * p).reshape(B, -1).sum(1)
+    g_logits = w * (g_w - S[:, None, None, None])
+    g_xf = np.einsum("bhwk,bak->bhwa", o["g_pts3d"].reshape(B, Hn, Wn, 3), M)
+    g_sel = g_xf * noc_scale[:, None, None, :] * dnoc                 # d/d logits[sel]
+    g_bin_s = np.zeros((B, C_, Hn, Wn))
+    for a in range(3):
+        np.put_along_axis(g_bin_s, sel[..., a][:, None], g_sel[..., a][:, None], 1)
+    g_bin = np.zeros((B, C_, H, W))
+    g_bin[sl] = g_bin_s
+    return dict(loss=o["loss"], g_bin_logits=g_bin, g_logits=g_logits, g_scale=S, pts3d=pts3d)

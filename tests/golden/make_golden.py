@@ -152,10 +152,57 @@ def make_dense():
         print(name, loss.detach().numpy(), os.path.getsize(path) // 1024, "KiB")
 
 
+def make_zebra():
+    """ZebraPose branch of dense_pose_loss (losses.py:355-356, 163-184, 16-45, 375, 383; floatbits.py:49-69, 99-160) and
+    the inference decode (floatbits.py:33-47, 197-224), run unmodified in fp64."""
+    import losses as ref_losses  # noqa: E402  (reference)
+    import floatbits as ref_fb   # noqa: E402  (reference)
+    from lc_b200.synth import make_zebra_outputs
+    for name, B, H, W, sample, tl, seed, bits, xf in (("zebra_b2_16x16_s2", 2, 16, 16, 2, (1, 0), 3, (5, 5, 5), False),
+                                                     ("zebra_b2_48x40_s3", 2, 48, 40, 3, (2, 1), 5, (7, 6, 5), True),
+                                                     ("zebra_b1_72x64_s3", 1, 72, 64, 3, (0, 2), 6, (7, 7, 6), True)):
+        d = make_zebra_outputs(B, H, W, seed, bits, with_transform=xf)
+        f64 = torch.float64
+        bl = d["bin_logits"].to(f64).requires_grad_(True)
+        lg = d["logits"].to(f64).requires_grad_(True)
+        sc = d["scale"].to(f64).requires_grad_(True)
+        T = None if d["model_transform"] is None else d["model_transform"].to(f64)
+        gt = dict(bit_cnt=list(bits))
+        if T is not None:
+            gt["model_transform"] = T
+        w_raw = lg.reshape(lg.shape[:-3] + (1, -1)).softmax(dim=-1)
+        weights = w_raw.reshape_as(lg) * sc
+        msk_vis = torch.ones(B, H, W, dtype=torch.bool)
+        ref_fb.set_black_background(True)
+        p2, inv_std, p3, _ = ref_losses.dense_pnp_matching_from_noc_bin(bl, d["raw_bits"], weights, msk_vis, d["msk_noc"],
+                                                                       d["noc_scale"].to(f64), gt, sample=sample, top_left=tl)
+        valid = torch.ones_like(p3[..., 0])
+        loss = Loss_cov_mixed(d["K"].to(f64), d["pose"].to(f64), p3, p2, inv_std, valid, bbox_3d=d["bbox_3d"].to(f64), max_err_len=32)
+        gb, gl, gs = torch.autograd.grad(loss.sum(), (bl, lg, sc))
+        with torch.no_grad():
+            noc_inf = ref_fb.nn_logits2noc(d["bin_logits"].to(f64), list(bits))
+            tgt_mod, tgt_raw = ref_fb.nn_noc2target(noc_inf, list(bits))
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(
+            path, in_bin_logits=d["bin_logits"].numpy(), in_raw_bits=d["raw_bits"].numpy(), in_msk_noc=d["msk_noc"].numpy(),
+            in_logits=d["logits"].numpy(), in_scale=d["scale"].numpy(), in_noc_scale=d["noc_scale"].numpy(), in_K=d["K"].numpy(),
+            in_pose=d["pose"].numpy(), in_bbox_3d=d["bbox_3d"].numpy(), bit_cnt=np.array(bits),
+            in_model_transform=np.zeros((0,), np.float32) if T is None else d["model_transform"].numpy(),
+            sample=np.array(sample), top_left=np.array(tl), ref_loss=loss.detach().numpy(), ref_pts3d=p3.detach().numpy(),
+            ref_g_bin_logits=gb.numpy().astype(np.float32), ref_g_logits=gl.numpy(), ref_g_scale=gs.numpy().reshape(B),
+            ref_noc_inference=noc_inf.numpy().astype(np.float32), ref_target_mod=np.packbits(tgt_mod.numpy()),
+            ref_target_raw=np.packbits(tgt_raw.numpy()))
+        print(name, loss.detach().numpy(), os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if "--only-zebra" in sys.argv:
+        make_zebra()
+        return
     make_jac_exact()
     make_dense()
+    make_zebra()
     for name, B, N, seed, vmode, regime, store_jac in CASES:
         d = build_inputs(B, N, seed, vmode, regime)
         o = run_reference(d)

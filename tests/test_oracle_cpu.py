@@ -120,3 +120,28 @@ def test_dense_producer_oracle_matches_reference_golden(oracle, name):
     assert rel_err(o["g_xyz_noc"], z["ref_g_xyz_noc"]) <= 1e-10
     assert rel_err(o["g_logits"], z["ref_g_logits"]) <= 1e-10
     assert np.abs(o["g_scale"] - z["ref_g_scale"]).max() <= 1e-10 * np.abs(z["ref_g_scale"]).max()
+
+
+ZEBRA_GOLDEN = ["zebra_b2_16x16_s2.npz", "zebra_b2_48x40_s3.npz", "zebra_b1_72x64_s3.npz"]
+
+
+@pytest.mark.parametrize("name", ZEBRA_GOLDEN)
+def test_zebra_producer_oracle_matches_reference_golden(oracle, name):
+    """oracle.dense_pose_loss_noc_bin / noc_bin_decode / noc_to_bits == the reference's ZebraPose branch of
+    dense_pose_loss (+ autograd), floatbits.nn_logits2noc and floatbits.nn_noc2target, run unmodified in fp64."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    T = z["in_model_transform"] if z["in_model_transform"].size else None
+    o = oracle.dense_pose_loss_noc_bin(z["in_bin_logits"], z["in_raw_bits"], z["in_msk_noc"], z["in_logits"], z["in_scale"],
+                                       z["in_noc_scale"], z["in_K"], z["in_pose"], z["in_bbox_3d"], z["bit_cnt"], int(z["sample"]),
+                                       tuple(z["top_left"]), T)
+    assert np.abs(o["loss"] - z["ref_loss"]).max() <= 1e-11 * np.abs(z["ref_loss"]).max()
+    assert rel_err(o["pts3d"], z["ref_pts3d"]) <= 1e-13
+    assert rel_err(o["g_bin_logits"], z["ref_g_bin_logits"]) <= 2e-7      # stored as fp32
+    assert rel_err(o["g_logits"], z["ref_g_logits"]) <= 1e-10
+    assert np.abs(o["g_scale"] - z["ref_g_scale"]).max() <= 1e-10 * np.abs(z["ref_g_scale"]).max()
+    noc = oracle.noc_bin_decode(z["in_bin_logits"], z["bit_cnt"])
+    assert np.abs(noc - z["ref_noc_inference"]).max() <= 1e-7             # stored as fp32
+    mod, raw = oracle.noc_to_bits(z["ref_noc_inference"].astype(np.float64), z["bit_cnt"])
+    assert np.array_equal(np.packbits(mod), z["ref_target_mod"]) and np.array_equal(np.packbits(raw), z["ref_target_raw"])
