@@ -7,6 +7,12 @@
 
 #include "lc_device.cuh"
 
+#ifdef LC_TIMING
+#define LC_MARK(k) do { if (threadIdx.x == 0) s.marks[k] = clock64(); } while (0)
+#else
+#define LC_MARK(k) do {} while (0)
+#endif
+
 namespace lc {
 
 enum { MODE_LM = 1, MODE_LC = 2 };
@@ -25,6 +31,7 @@ struct LmState {
 struct PoseShared {
     double K[9], pose[7], R[9], Rb[9], t[3], bbox[24];
     double Tm[36];  // accumulation basis -> reference (right-perturbation) basis: J_ref = J_acc . Tm
+    double Ti[36];  // Tm^-1 (lc_six_warp works in the accumulation basis: rows_acc = rows . Ti)
     double red[kMaxWarps * 48];
     double fin[48];
     double H[36], G[36], C[36], M[36], T1[36], T2[36], Cbar[36], Mbar[36], Gbar[36], Hbar[36];
@@ -34,6 +41,10 @@ struct PoseShared {
     double cHL[kSym], cGL[kSym], bL[6];  // reverse-pass coefficients, left basis, packed (off-diagonals doubled)
     int flag, pad;
     unsigned long long tma_bar;  // mbarrier of the TMA staging (lc_resident.cu)
+#ifdef LC_TIMING
+    long long fin_timing[8];     // cycles per phase (thread 0): stage, lm pass, lm advance, lc setup, lc passes 1-3, six, pass 4
+    long long marks[48];         // clock64() at the barriers of the 6x6 sections (LC_MARK)
+#endif
     LmState lm;
 };
 
@@ -357,6 +368,7 @@ __device__ inline void lc_pose_setup(PoseShared& s, bool decouple_depth) {   // 
 template <typename T, int NT>
 __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, int b) {
     const int tid = threadIdx.x;
+    LC_MARK(0);
     for (int e = tid; e < 36; e += NT) {
         const int r = e / 6, c = e % 6;
         s.H[e] = tts_gen(s.fin, s.Tm, r, c);
@@ -377,7 +389,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
             s.rows[tid * 6 + 3 + cc] = (r == cc) ? 1.0 : 0.0;
         }
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(1);
     if (tid == 0) {
         // safe_cholesky: non-SPD -> identity (pnp_utils.py:140-167)
         double Hs[36];
@@ -388,16 +400,16 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
             for (int k = 0; k < 36; ++k) s.C[k] = (k % 7 == 0) ? 1.0 : 0.0;
         }
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(2);
     mm6_par<NT>(s.C, s.G, s.T1);
     if (tid < 6) {
         double v = 0.0;
         for (int k = 0; k < 6; ++k) v = fma(s.C[tid * 6 + k], s.bv[k], v);
         s.dth[tid] = v;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(3);
     mm6_par<NT>(s.T1, s.C, s.M);  // M = C G C
-    __syncthreads();
+    __syncthreads(); LC_MARK(4);
     if (tid < 24) {
         const double* row = s.rows + tid * 6;
         double vc = 0.0, vm = 0.0, uu = 0.0;
@@ -408,7 +420,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         }
         s.vC[tid] = vc; s.vM[tid] = vm; s.u[tid] = uu;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(5);
     // per-corner sums on 8 threads, then the scalar loss on one
     if (tid < 8) {
         const int j = tid;
@@ -422,7 +434,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         if (!goodC) s.flag |= LC_ST_PRIOR_NOT_GOOD;
         if (!goodM) s.flag |= LC_ST_COV_NOT_GOOD;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(6);
     const bool goodC = !(s.flag & LC_ST_PRIOR_NOT_GOOD), goodM = !(s.flag & LC_ST_COV_NOT_GOOD);
     double rsC = 0.0, rsM = 0.0, un = 0.0;
     if (tid < 8) {
@@ -433,7 +445,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         s.T1[tid] = goodC ? s.wC[tid] * rsC : 1.0;        // sqrt terms of prior
         s.T1[8 + tid] = goodM ? s.wM[tid] * rsM : 1.0;    // sqrt terms of cov_err
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(7);
     if (tid < 8) {
         double prior = 0.0, cov_err = 0.0, lin = 0.0;
         for (int j = 0; j < 8; ++j) { prior += s.T1[j]; cov_err += s.T1[8 + j]; lin += s.wU[j]; }
@@ -452,7 +464,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         s.T2[8 + tid] = goodM ? g_c * 0.0625 * rsM : 0.0;
         s.T2[16 + tid] = un > 0.0 ? g_c * 0.125 * fast_rcp(un) : 0.0;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(8);
     if (tid < 8) { s.wC[tid] = s.T2[tid]; s.wM[tid] = s.T2[8 + tid]; s.wU[tid] = s.T2[16 + tid]; }
     if (a.cov.ptr)
         for (int e = tid; e < 36; e += NT) st<T>(a.cov, b * a.cov.stride[0] + (e / 6) * a.cov.stride[1] + (e % 6) * a.cov.stride[2], s.C[e]);
@@ -460,7 +472,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
         for (int e = tid; e < 36; e += NT)
             st<T>(a.update_cov, b * a.update_cov.stride[0] + (e / 6) * a.update_cov.stride[1] + (e % 6) * a.update_cov.stride[2],
                   0.5 * (s.M[e] + s.M[(e % 6) * 6 + e / 6]));
-    __syncthreads();
+    __syncthreads(); LC_MARK(9);
 }
 
 // Reverse 6x6 section: fills s.cHL, s.cGL, s.bL (left basis, symmetrised, off-diagonals doubled,
@@ -483,7 +495,7 @@ __device__ __forceinline__ void lc_six_backward(PoseShared& s) {
         for (int k = 0; k < 24; ++k) v = fma(s.wU[k / 3] * s.u[k], s.rows[k * 6 + tid], v);
         s.dthbar[tid] = v;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(10);
     mm6_par<NT>(s.C, s.Mbar, s.T1);   // C Mbar
     mm6_par<NT>(s.Mbar, s.C, s.T2);   // Mbar C
     if (tid < 6) {
@@ -491,22 +503,22 @@ __device__ __forceinline__ void lc_six_backward(PoseShared& s) {
         for (int k = 0; k < 6; ++k) v = fma(s.C[tid * 6 + k], s.dthbar[k], v);
         s.bbar[tid] = v;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(11);
     mm6_par<NT>(s.T1, s.C, s.Gbar);   // Gbar = C Mbar C
     mm6_par<NT>(s.T2, s.G, s.Hbar);   // (Mbar C G), staged in Hbar
-    __syncthreads();
+    __syncthreads(); LC_MARK(12);
     for (int e = tid; e < 36; e += NT) {
         const int r = e / 6, c = e % 6;
         s.T1[e] = s.Cbar[e] + s.Hbar[e] + s.Hbar[c * 6 + r] + s.dthbar[r] * s.bv[c];  // Cbar total
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(13);
     mm6_par<NT>(s.C, s.T1, s.T2);
-    __syncthreads();
+    __syncthreads(); LC_MARK(14);
     mm6_par<NT>(s.T2, s.C, s.Hbar);   // -Hbar
-    __syncthreads();
+    __syncthreads(); LC_MARK(15);
     if (s.flag & LC_ST_HESS_NOT_SPD)
         for (int e = tid; e < 36; e += NT) s.Hbar[e] = 0.0;   // torch.where(cond, eye, H): no gradient into H
-    __syncthreads();
+    __syncthreads(); LC_MARK(16);
     // to the accumulation basis, symmetrised and packed with doubled off-diagonals: J^T S J = sum_{i<=j} c_ij J'_i J'_j
     for (int e = tid; e < kSym * 2; e += NT) {
         const bool isG = e >= kSym;
@@ -526,7 +538,250 @@ __device__ __forceinline__ void lc_six_backward(PoseShared& s) {
         for (int j = 0; j < 6; ++j) v = fma(s.Tm[tid * 6 + j], s.bbar[j], v);   // bL = Tm bbar
         s.bL[tid] = v;
     }
-    __syncthreads();
+    __syncthreads(); LC_MARK(17);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Warp-synchronous 6x6 sections (resident kernels).  Same math as lc_six_forward / lc_six_backward, but
+//   * carried out in the ACCUMULATION basis: with H_ref = Tm^T H' Tm the corner quantities J_b C_ref J_b^T equal
+//     (J_b Tm^-1) C' (J_b Tm^-1)^T, so the bbox rows are mapped once (rows' = rows . Tm^-1) and H', G', b' are used as
+//     accumulated; the reverse coefficients then come out in the accumulation basis directly (no basis transforms);
+//   * executed by ONE warp with __syncwarp() between stages (the other warps wait at a single CTA barrier), the 6x6
+//     inverse by an in-place Gauss-Jordan sweep over the warp (pivots = the LDL^T pivots, so the SPD test of
+//     safe_cholesky, pnp_utils.py:140-167, is the same leading-minor test).
+// ---------------------------------------------------------------------------------------------
+__device__ inline void lc_pose_setup_acc(PoseShared& s) {   // one thread, after lc_pose_setup: Ti = blockdiag(R^-1, Ut)
+    const double* R = s.R;
+    const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
+    const double idet = 1.0 / (R[0] * c00 + R[1] * c01 + R[2] * c02);
+    for (int k = 0; k < 36; ++k) s.Ti[k] = 0.0;
+    s.Ti[0] = c00 * idet; s.Ti[1] = (R[2] * R[7] - R[1] * R[8]) * idet; s.Ti[2] = (R[1] * R[5] - R[2] * R[4]) * idet;
+    s.Ti[6] = c01 * idet; s.Ti[7] = (R[0] * R[8] - R[2] * R[6]) * idet; s.Ti[8] = (R[2] * R[3] - R[0] * R[5]) * idet;
+    s.Ti[12] = c02 * idet; s.Ti[13] = (R[1] * R[6] - R[0] * R[7]) * idet; s.Ti[14] = (R[0] * R[4] - R[1] * R[3]) * idet;
+    s.Ti[21] = 1.0; s.Ti[28] = 1.0; s.Ti[35] = 1.0;
+    s.Ti[23] = -s.Tm[23]; s.Ti[29] = -s.Tm[29];
+}
+
+// In-place inverse of the SPD 6x6 A (shared, row-major) by one warp.  Returns 0, or the order of the first
+// non-positive leading minor.  Every lane owns entry `lane` (and lanes 0..3 also entry 32 + lane).
+__device__ __forceinline__ int inv6_warp(double* A, int lane) {
+    const int r0 = lane / 6, c0 = lane % 6, e1 = 32 + lane, c1 = 2 + lane;   // entry e1 = (5, 2 + lane) for lane < 4
+    const bool two = lane < 4;
+    for (int p = 0; p < 6; ++p) {
+        const double d = A[p * 7];
+        if (!(d > 0.0) || isinf(d)) return p + 1;   // uniform: every lane reads the same pivot
+        const double ip = fast_rcp(d);
+        const double a0 = A[lane], rp0 = A[p * 6 + c0], cp0 = A[r0 * 6 + p];
+        double a1 = 0.0, rp1 = 0.0, cp1 = 0.0;
+        if (two) { a1 = A[e1]; rp1 = A[p * 6 + c1]; cp1 = A[30 + p]; }
+        __syncwarp();
+        auto upd = [&](int r, int c, double a, double rowp, double colp) {
+            if (r == p) return c == p ? ip : rowp * ip;
+            if (c == p) return -colp * ip;
+            return fma(-colp * ip, rowp, a);
+        };
+        if (lane < 36) A[lane] = upd(r0, c0, a0, rp0, cp0);
+        if (two) A[e1] = upd(5, c1, a1, rp1, cp1);
+        __syncwarp();
+    }
+    return 0;
+}
+
+// O = A B (6x6, shared) by one warp; caller synchronises
+__device__ __forceinline__ void mm6_warp(const double* A, const double* B, double* O, int lane) {
+    for (int e = lane; e < 36; e += 32) {
+        const int r = e / 6, c = e % 6;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v = fma(A[r * 6 + k], B[k * 6 + c], v);
+        O[e] = v;
+    }
+}
+
+// Called by warp 0 (all 32 lanes converged).  In: s.fin[0..48) = H', G' (packed), b'.  Writes the loss / flags / optional
+// covariances and, when want_grads, s.cHL, s.cGL, s.bL.  The caller follows with a CTA barrier.
+template <typename T>
+__device__ __forceinline__ void lc_six_warp(const lc_args& a, PoseShared& s, int b, bool want_grads) {
+    const int lane = threadIdx.x & 31;
+    const double* bacc = s.fin + 42;
+    LC_MARK(0);
+    // ---- unpack H', G'; bbox rows in the accumulation basis: [Rb(-[c_j]x) R^-1 | rows of Ut]  (cov_mixed.py:52-65) ----
+    for (int e = lane; e < 36; e += 32) {
+        const int r = e / 6, c = e % 6, k = r <= c ? sym_idx(r, c) : sym_idx(c, r);
+        s.H[e] = s.fin[k];
+        s.C[e] = s.fin[k];
+        s.G[e] = s.fin[21 + k];
+    }
+    if (lane < 24) {
+        const int j = lane / 3, r = lane % 3;
+        const double* c = s.bbox + 3 * j;
+        const double nC[9] = {0, c[2], -c[1], -c[2], 0, c[0], c[1], -c[0], 0};
+        double A3[3];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) A3[cc] = s.Rb[r * 3] * nC[cc] + s.Rb[r * 3 + 1] * nC[3 + cc] + s.Rb[r * 3 + 2] * nC[6 + cc];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) s.rows[lane * 6 + m] = A3[0] * s.Ti[m] + A3[1] * s.Ti[6 + m] + A3[2] * s.Ti[12 + m];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) s.rows[lane * 6 + 3 + m] = s.Ti[(3 + r) * 6 + 3 + m];
+    }
+    __syncwarp();
+    LC_MARK(1);
+    // ---- C' = H'^-1; non-SPD -> H_ref := I (pnp_utils.py:140-158), i.e. C' = Tm Tm^T ----
+    const int info = inv6_warp(s.C, lane);
+    if (info != 0) {
+        if (lane == 0) s.flag |= LC_ST_HESS_NOT_SPD;
+        __syncwarp();
+        for (int e = lane; e < 36; e += 32) {
+            const int r = e / 6, c = e % 6;
+            double v = 0.0;
+            for (int k = 0; k < 6; ++k) v = fma(s.Tm[r * 6 + k], s.Tm[c * 6 + k], v);
+            s.C[e] = v;
+        }
+        __syncwarp();
+    }
+    LC_MARK(2);
+    mm6_warp(s.C, s.G, s.T1, lane);
+    if (lane < 6) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v = fma(s.C[lane * 6 + k], bacc[k], v);
+        s.dth[lane] = v;
+        s.bv[lane] = bacc[lane];
+    }
+    __syncwarp();
+    mm6_warp(s.T1, s.C, s.M, lane);   // M' = C' G' C'
+    __syncwarp();
+    LC_MARK(3);
+    // ---- per bbox-corner coordinate: prior variance, propagated variance, linear term (cov_mixed.py:68-89, 146) ----
+    double vc = 1.0, vm = 1.0, uu = 0.0;
+    if (lane < 24) {
+        const double* row = s.rows + lane * 6;
+        vc = 0.0; vm = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double wc = 0.0, wm = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { wc = fma(s.C[r * 6 + c], row[c], wc); wm = fma(s.M[r * 6 + c], row[c], wm); }
+            vc = fma(row[r], wc, vc); vm = fma(row[r], wm, vm); uu = fma(row[r], s.dth[r], uu);
+        }
+        s.u[lane] = uu;
+    }
+    const bool goodC = __all_sync(kFull, vc > 0.0), goodM = __all_sync(kFull, vm > 0.0);
+    if (lane == 0) s.flag |= (goodC ? 0 : LC_ST_PRIOR_NOT_GOOD) | (goodM ? 0 : LC_ST_COV_NOT_GOOD);
+    // corner sums: lanes 3j, 3j+1, 3j+2 -> lane 3j
+    const double wCj = vc + __shfl_down_sync(kFull, vc, 1) + __shfl_down_sync(kFull, vc, 2);
+    const double wMj = vm + __shfl_down_sync(kFull, vm, 1) + __shfl_down_sync(kFull, vm, 2);
+    const double u2 = uu * uu;
+    const double wUj = u2 + __shfl_down_sync(kFull, u2, 1) + __shfl_down_sync(kFull, u2, 2);
+    // lane L < 24: group g = L / 8 (0 prior, 1 cov_err, 2 lin), corner j = L % 8: fetch that corner's sum from lane 3j
+    const int g = lane >> 3, j = lane & 7;
+    const double sC = __shfl_sync(kFull, wCj, 3 * j), sM = __shfl_sync(kFull, wMj, 3 * j), sU = __shfl_sync(kFull, wUj, 3 * j);
+    // sqrt(x) = x * rsqrt(x); one rsqrt for all three groups (no divergent branches in the serial section)
+    const double xg = g == 0 ? sC : (g == 1 ? sM : sU);
+    const bool live = g == 0 ? goodC : (g == 1 ? goodM : (g == 2 && xg > 0.0));
+    double rs = live ? rsqrt(xg) : (g == 2 ? 0.0 : 1.0);
+    double term = live ? xg * rs : (g < 2 ? 1.0 : 0.0);   // sqrt term of this lane's (group, corner); rs = its reciprocal
+    double sum = term;
+    sum += __shfl_xor_sync(kFull, sum, 1);
+    sum += __shfl_xor_sync(kFull, sum, 2);
+    sum += __shfl_xor_sync(kFull, sum, 4);
+    const double prior = 0.125 * __shfl_sync(kFull, sum, 0), cov_err = 0.125 * __shfl_sync(kFull, sum, 8),
+                 lin = 0.125 * __shfl_sync(kFull, sum, 16);
+    const double ip = fast_rcp(prior);
+    const double go = a.grad_scale * (a.grad_out.ptr ? ld<T>(a.grad_out, b * a.grad_out.stride[0]) : 1.0);
+    const double g_p = go * (ip - 0.5 * (cov_err + lin) * ip * ip);
+    const double g_c = go * 0.5 * ip;
+    if (lane == 0) {
+        const double loss = log(prior) + 0.5 * (cov_err + lin) * ip;
+        if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], loss);
+        if (a.lc_flags) a.lc_flags[b] = s.flag;
+        if (a.loss_sum) { atomicAdd(a.loss_sum, loss); atomicAdd(a.loss_sum + 1, 1.0); }
+    }
+    if (g == 0) s.wC[j] = goodC ? g_p * 0.0625 * rs : 0.0;
+    else if (g == 1) s.wM[j] = goodM ? g_c * 0.0625 * rs : 0.0;
+    else if (g == 2) s.wU[j] = g_c * 0.125 * rs;
+    if (a.cov.ptr || a.update_cov.ptr) {
+        // reference-basis covariances on request: S_ref = Tm^-1 S' Tm^-T
+        for (int e = lane; e < 36; e += 32) {
+            const int r = e / 6, c = e % 6;
+            double vC = 0.0, vM = 0.0;
+            for (int i = 0; i < 6; ++i) {
+                double wc = 0.0, wm = 0.0;
+                for (int k = 0; k < 6; ++k) { wc = fma(s.C[i * 6 + k], s.Ti[c * 6 + k], wc); wm = fma(0.5 * (s.M[i * 6 + k] + s.M[k * 6 + i]), s.Ti[c * 6 + k], wm); }
+                vC = fma(s.Ti[r * 6 + i], wc, vC); vM = fma(s.Ti[r * 6 + i], wm, vM);
+            }
+            if (a.cov.ptr) st<T>(a.cov, b * a.cov.stride[0] + r * a.cov.stride[1] + c * a.cov.stride[2], vC);
+            if (a.update_cov.ptr) st<T>(a.update_cov, b * a.update_cov.stride[0] + r * a.update_cov.stride[1] + c * a.update_cov.stride[2], vM);
+        }
+    }
+    __syncwarp();
+    LC_MARK(4);
+    if (!want_grads) return;
+
+    // ---- reverse ----
+    if (lane < kSym) {
+        int r = 0, c = lane;
+        while (c >= 6 - r) { c -= 6 - r; ++r; }
+        c += r;                                                   // packed index lane -> (r, c), r <= c
+        double cb = 0.0, mb = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 24; ++k) {
+            const double qq = s.rows[k * 6 + r] * s.rows[k * 6 + c];
+            cb = fma(s.wC[k / 3], qq, cb);
+            mb = fma(s.wM[k / 3], qq, mb);
+        }
+        s.Cbar[r * 6 + c] = cb; s.Cbar[c * 6 + r] = cb;
+        s.Mbar[r * 6 + c] = mb; s.Mbar[c * 6 + r] = mb;
+    } else if (lane < kSym + 6) {
+        const int t = lane - kSym;
+        double v = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 24; ++k) v = fma(s.wU[k / 3] * s.u[k], s.rows[k * 6 + t], v);
+        s.dthbar[t] = v;
+    }
+    __syncwarp();
+    LC_MARK(5);
+    mm6_warp(s.C, s.Mbar, s.T1, lane);   // C Mbar  (Mbar C is its transpose: both factors are symmetric)
+    if (lane < 6) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v = fma(s.C[lane * 6 + k], s.dthbar[k], v);
+        s.bbar[lane] = v;
+    }
+    __syncwarp();
+    mm6_warp(s.T1, s.C, s.Gbar, lane);   // Gbar = C Mbar C
+    for (int e = lane; e < 36; e += 32) {  // (Mbar C) G = T1^T G, staged in Hbar
+        const int r = e / 6, c = e % 6;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v = fma(s.T1[k * 6 + r], s.G[k * 6 + c], v);
+        s.Hbar[e] = v;
+    }
+    __syncwarp();
+    for (int e = lane; e < 36; e += 32) {
+        const int r = e / 6, c = e % 6;
+        s.T2[e] = s.Cbar[e] + s.Hbar[e] + s.Hbar[c * 6 + r] + s.dthbar[r] * s.bv[c];  // Cbar total
+    }
+    __syncwarp();
+    mm6_warp(s.C, s.T2, s.T1, lane);
+    __syncwarp();
+    mm6_warp(s.T1, s.C, s.Hbar, lane);   // -Hbar
+    __syncwarp();
+    LC_MARK(6);
+    const bool spd = !(s.flag & LC_ST_HESS_NOT_SPD);   // torch.where(cond, eye, H): no gradient into H
+    if (lane < kSym) {
+        int r = 0, c = lane;
+        while (c >= 6 - r) { c -= 6 - r; ++r; }
+        c += r;
+        double h = -s.Hbar[r * 6 + c], gg = s.Gbar[r * 6 + c];
+        if (r != c) { h -= s.Hbar[c * 6 + r]; gg += s.Gbar[c * 6 + r]; }
+        s.cHL[lane] = spd ? h : 0.0;
+        s.cGL[lane] = gg;
+    } else if (lane < kSym + 6) {
+        s.bL[lane - kSym] = s.bbar[lane - kSym];
+    }
+    LC_MARK(7);
 }
 
 // host-side launch entry points implemented in lc_stream.cu / lc_resident.cu (return cudaError_t as int)

@@ -24,7 +24,7 @@
 namespace lc {
 
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
+__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
     const ResLayout l = res_layout(smem_raw, npad);
@@ -32,6 +32,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args
     const int tid = threadIdx.x;
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
+#ifdef LC_TIMING
+    if (tid == 0) for (int k = 0; k < 8; ++k) s.fin_timing[k] = 0;
+    const long long t_begin = clock64();
+#endif
+    { LC_TIC(tq1);
 
     // ---- stage the correspondences.  Planar, 16-byte aligned arrays (what the dense call site produces, tma_mask
     //      bit 0 = pts3d, bit 1 = pts2d) go through the TMA: one 1-D bulk copy per component slab, issued by one
@@ -50,6 +55,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args
                 mbar_expect_tx(&s.tma_bar, slab * ((tma3 ? 3u : 0u) + (tma2 ? 2u : 0u)));
                 if (tma3) { tma_load_1d(l.A0, p3, slab, &s.tma_bar); tma_load_1d(l.A1, p3 + s3c, slab, &s.tma_bar); tma_load_1d(l.A2, p3 + 2 * s3c, slab, &s.tma_bar); }
                 if (tma2) { tma_load_1d(l.B0, p2, slab, &s.tma_bar); tma_load_1d(l.B1, p2 + s2c, slab, &s.tma_bar); }
+                if (tma_mask & 4) {   // planar 16-byte aligned weights: two slabs into L2 ahead of their first use
+                    const float* pw = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
+                    l2_prefetch_bulk(pw, slab);
+                    l2_prefetch_bulk(pw + a.weights.stride[2], slab);
+                }
             }
         }
         if (!(tma3 && tma2)) {
@@ -86,11 +96,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args
         }
     }
     __syncthreads();
+    LC_TOC(tq1, 0); }
 
     // =========================== LM solve (fp64) ===========================
     if (MODE & MODE_LM) {
         LmState& L = s.lm;
+#ifdef LC_TIMING
+        double* trace = nullptr;
+#else
         double* trace = a.trace ? a.trace + (int64_t)b * (a.max_iter + 2) * 4 : nullptr;
+#endif
         bool solved = false;
         if (n >= 3) {
             if (tid == 0) {
@@ -103,12 +118,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args
             bool first = true;
             for (;;) {
                 const int kind = L.ctl;
+                { LC_TIC(tq2);
                 if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(a, s, l, b, n, sanitize);
                 else lm_eval_pass_res<NT, true>(a, s, l, b, n, sanitize);
+                LC_TOC(tq2, 1); }
+                LC_TIC(tq3);
                 if (tid == 0)
                     lm_advance(L, s.fin, kind, first, a.max_iter, a.function_tolerance, (a.flags & LC_FLAG_TOL_NEEDS_SUCCESS) != 0, trace);
                 first = false;
                 __syncthreads();
+                LC_TOC(tq3, 2);
                 if (L.ctl == CTL_STOP) break;
             }
             solved = L.term == TERM_CONVERGENCE;
@@ -116,12 +135,23 @@ __global__ void __launch_bounds__(NT, 512 / NT) lc_resident_kernel(const lc_args
         if (tid == 0) lm_write_result<float>(a, s, b, n, solved);
         __syncthreads();
     }
+#ifdef LC_TIMING
+    if (!(MODE & MODE_LC)) {
+        if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin); }
+        return;
+    }
+#else
     if (!(MODE & MODE_LC)) return;
+#endif
 
     // =========================== LC loss ===========================
     const DirectWeights wsrc{static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0], a.weights.stride[1], a.weights.stride[2]};
     DirectSink sink{a, b};
     lc_phase_res<NT>(a, s, l, b, n, wsrc, sink);
+#ifdef LC_TIMING
+    if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
+        for (int k = 0; k < 40; ++k) tr[8 + k] = (double)(s.marks[k] - s.marks[0]); }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -165,7 +195,9 @@ static bool tma_ok(const lc_view& v, int n) {
 }
 static int tma_mask_for(const lc_args& a) {
     if (getenv("LC_B200_NO_TMA")) return 0;
-    return (tma_ok(a.pts3d, a.N) ? 1 : 0) | (tma_ok(a.pts2d, a.N) ? 2 : 0);
+    const int m = (tma_ok(a.pts3d, a.N) ? 1 : 0) | (tma_ok(a.pts2d, a.N) ? 2 : 0);
+    const bool w_planar = (a.weight_mode == LC_W_ICOV_DIAG || a.weight_mode == LC_W_INV_STD) && tma_ok(a.weights, a.N);
+    return m | ((m && w_planar && !getenv("LC_B200_NO_L2PF")) ? 4 : 0);
 }
 
 template <int NT, int MODE>
@@ -187,7 +219,10 @@ template <int MODE>
 static int launch_res_m(const lc_args& a, cudaStream_t st) {
     // 256 threads x 2 CTAs per SM (20 B/point of shared memory): one CTA's 6x6 / trust-region sections and loads
     // overlap the other CTA's point passes
-    if (resident_threads_for(a.N, MODE) == 128) return launch_res_t<128, MODE>(a, st);
+    const int nt = resident_threads_for(a.N, MODE);
+    if (nt == 128) return launch_res_t<128, MODE>(a, st);
+    if (nt == 192) return launch_res_t<192, MODE>(a, st);
+    if (nt == 320) return launch_res_t<320, MODE>(a, st);
     return launch_res_t<256, MODE>(a, st);
 }
 

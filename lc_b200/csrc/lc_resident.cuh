@@ -9,6 +9,16 @@
 
 namespace lc {
 
+// Phase timing for tools/phase_timing.py (build with -DLC_TIMING): thread 0 accumulates clock64() deltas per phase and
+// the resident kernel writes them to lc_args.trace[b*stride + 0..7].  Compiled out of the product build.
+#ifdef LC_TIMING
+#define LC_TIC(v) const long long v = clock64()
+#define LC_TOC(v, slot) do { if (threadIdx.x == 0) s.fin_timing[slot] += clock64() - v; } while (0)
+#else
+#define LC_TIC(v) do {} while (0)
+#define LC_TOC(v, slot) do {} while (0)
+#endif
+
 constexpr int kResidentMinN = 65;
 
 __host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
@@ -60,6 +70,11 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Ask the L2 to fetch a contiguous slab (cp.async.bulk.prefetch.L2): the weights are not staged in shared memory, this
+// makes their first pass an L2 hit instead of an HBM round trip.  bytes must be a multiple of 16, the address 16-byte aligned.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
     unsigned done = 0;
@@ -163,8 +178,11 @@ struct DirectSink {      // gradients written to the strided views of lc_args
 template <int NT, class WSrc, class Sink>
 __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, const WSrc& wsrc, Sink& sink) {
     const int tid = threadIdx.x;
-    if (tid == 0) lc_pose_setup(s, true);
+    { LC_TIC(tq1);
+    if (tid == 0) { lc_pose_setup(s, true); lc_pose_setup_acc(s); }
     __syncthreads();
+    LC_TOC(tq1, 3); }
+    LC_TIC(tq2);
 
     const int64_t ovb = a.valid.ptr ? b * a.valid.stride[0] : 0;
     // pass 1 (fp64): P = R X + t, project_apply + clamp_error once per point; P, ec kept as fp32 in place
@@ -280,9 +298,13 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
         for (int k = 0; k < 48; ++k) accd[k] = acc[k];
         block_reduce<48, NT>(accd, s.red, s.fin);
     }
-    lc_six_forward<float, NT>(a, s, b);
+    LC_TOC(tq2, 4);
+    { LC_TIC(tq3);
+    if (tid < 32) lc_six_warp<float>(a, s, b, sink.want_any());
+    __syncthreads();
     if (!sink.want_any()) return;
-    lc_six_backward<NT>(s);
+    LC_TOC(tq3, 5); }
+    LC_TIC(tq4);
 
     // pass 4 (fp32): per-coordinate adjoints and the three input gradients
     {
@@ -342,6 +364,10 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
             }
         }
     }
+#ifdef LC_TIMING
+    __syncthreads();
+#endif
+    LC_TOC(tq4, 6);
 }
 
 }  // namespace lc
