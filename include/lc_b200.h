@@ -182,6 +182,42 @@ typedef struct lc_decode_args {
 
 int lc_b200_noc_bin_decode(const lc_decode_args* a, void* cuda_stream);
 
+/*
+ * Test-time point selection ("next" row f2): the selection half of test.solve_pnp_dense (test.py:67-119) on the device.
+ *   weights  = softmax(weight logits over 2*H*W, or per channel when weights_scale is (B,2)) * weights_scale   test.py:84-88
+ *   sub-sample every `sample`-th pixel from (0,0): pts2d grid, inv_std, xyz, seg mask                           losses.py:142-161
+ *   inv_cov  = inv_std^2                                                                                        test.py:95
+ *   valid    = mask | quantile | quantile_in_mask (torch.quantile, linear interpolation, fp32)                  test.py:36-45, 97-104
+ *   v.nonzero() -> ragged lists -> cer_solver._batch_tensors zero padding                                       test.py:106-119,
+ *                                                                                                               cer_solver.py:67-87
+ * Output: zero-padded (B,Nmax,.) correspondences in selection order + n_points (B): the inputs of lc_b200_lm_solve, with
+ * no device->host synchronisation.  Samples with fewer than min_points (4) selected points are padded with pseudo-random
+ * indices (test.py:108-113 draws them from np.random).  `weights` may carry the precomputed inv_std map instead of
+ * logits + scale (then the selection is bit-exact w.r.t. the reference given the same map).
+ */
+enum { LC_SEL_MASK = 0, LC_SEL_QUANTILE = 1, LC_SEL_QUANTILE_IN_MASK = 2 };
+
+typedef struct lc_select_args {
+    int32_t abi_version, B, H, W;
+    int32_t sample, mode, scale_dim, min_points; /* mode: LC_SEL_*; scale_dim 1 (joint softmax) or 2 (per channel); min_points 4 */
+    int32_t Nmax, reserved0;                     /* Nmax = ceil(H/sample)*ceil(W/sample) */
+    float quantile, one_minus_quantile;          /* cfg.quantile and (float)(1 - cfg.quantile) */
+    float seg_thresh, reserved1;                 /* cfg.seg_thresh (0.5) */
+    lc_view xyz;           /* (B,H,W,3) fp32, any strides [batch,row,col,component] (nn_out_to_xyz output or an NCHW permute) */
+    lc_view noc_scale;     /* (B,3) multiplier or NULL */
+    lc_view weights;       /* (B,2,H,W) precomputed inv_std, any strides, or NULL */
+    lc_view logits;        /* (B,2,H,W) weight logits, contiguous (H,W) planes (when weights is NULL) */
+    lc_view weights_scale; /* (B,scale_dim) */
+    lc_view msk_logits;    /* (B,H,W) msk_vis_logits, strides [batch,row,col] */
+    lc_view pts3d;         /* out (B,Nmax,3) */
+    lc_view pts2d;         /* out (B,Nmax,2) */
+    lc_view inv_cov;       /* out (B,Nmax,2) */
+    int32_t* index;        /* out (B,Nmax) sampled-point index of every slot (-1 = padding), or NULL */
+    int32_t* n_points;     /* out (B) */
+} lc_select_args;
+
+int lc_b200_dense_select(const lc_select_args* a, void* cuda_stream);
+
 int lc_b200_abi_version(void);
 const char* lc_b200_last_error(void);
 

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("LC_B200_LIB") or os.path.join(_HERE, "liblc_b200.so")   # env override: instrumented builds (tools/)
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu", "lc_select.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "csrc", "lc_pose.cuh"),
            os.path.join(_HERE, "csrc", "lc_resident.cuh"),
            os.path.join(_ROOT, "include", "lc_b200.h")]
@@ -31,7 +31,7 @@ ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
            "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd",
-           "lc_b200_dense_loss_fwd_bwd", "lc_b200_noc_bin_decode")
+           "lc_b200_dense_loss_fwd_bwd", "lc_b200_noc_bin_decode", "lc_b200_dense_select")
 
 
 class NativeLibraryError(RuntimeError):
@@ -84,6 +84,18 @@ class lc_decode_args(C.Structure):
                 ("noc_bin_logits", lc_view), ("noc_scale", lc_view), ("model_transform", lc_view), ("xyz", lc_view)]
 
 
+SEL_MASK, SEL_QUANTILE, SEL_QUANTILE_IN_MASK = 0, 1, 2
+
+
+class lc_select_args(C.Structure):
+    _fields_ = ([("abi_version", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                 ("sample", C.c_int32), ("mode", C.c_int32), ("scale_dim", C.c_int32), ("min_points", C.c_int32),
+                 ("Nmax", C.c_int32), ("reserved0", C.c_int32), ("quantile", C.c_float), ("one_minus_quantile", C.c_float),
+                 ("seg_thresh", C.c_float), ("reserved1", C.c_float)]
+                + [(f, lc_view) for f in ("xyz", "noc_scale", "weights", "logits", "weights_scale", "msk_logits", "pts3d", "pts2d", "inv_cov")]
+                + [("index", C.c_void_p), ("n_points", C.c_void_p)])
+
+
 def nvcc_commands(out: str = LIB_PATH):
     """One `nvcc -c` per translation unit (run in parallel) and the final link."""
     objs = [os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o") for src in SOURCES]
@@ -130,7 +142,8 @@ def lib() -> C.CDLL:
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name}")
         handle.lc_b200_last_error.restype = C.c_char_p
         for name in EXPORTS[3:]:
-            argt = {"lc_b200_dense_loss_fwd_bwd": lc_dense_args, "lc_b200_noc_bin_decode": lc_decode_args}.get(name, lc_args)
+            argt = {"lc_b200_dense_loss_fwd_bwd": lc_dense_args, "lc_b200_noc_bin_decode": lc_decode_args,
+                    "lc_b200_dense_select": lc_select_args}.get(name, lc_args)
             getattr(handle, name).argtypes = [C.POINTER(argt), C.c_void_p]
             getattr(handle, name).restype = C.c_int
         if handle.lc_b200_abi_version() != ABI_VERSION:

@@ -104,6 +104,27 @@ static int dispatch_decode(const lc_decode_args* d, void* stream) {
     return check_launch(launch_decode(*d, static_cast<cudaStream_t>(stream)));
 }
 
+static int dispatch_select(const lc_select_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->sample <= 0) return fail(LC_E_BADARG, "bad B / H / W / sample");
+    if (d->mode < LC_SEL_MASK || d->mode > LC_SEL_QUANTILE_IN_MASK) return fail(LC_E_BADARG, "bad selection mode");
+    if (d->scale_dim != 1 && d->scale_dim != 2) return fail(LC_E_BADARG, "scale_dim must be 1 or 2");
+    const int N = ((d->H + d->sample - 1) / d->sample) * ((d->W + d->sample - 1) / d->sample);
+    if (d->Nmax < N || d->min_points < 0 || d->min_points > 32) return fail(LC_E_BADARG, "Nmax too small or bad min_points");
+    if (d->B == 0) return LC_OK;
+    if (!d->xyz.ptr || !d->msk_logits.ptr || !d->pts3d.ptr || !d->pts2d.ptr || !d->inv_cov.ptr || !d->n_points)
+        return fail(LC_E_NULL, "xyz, msk_logits, pts3d, pts2d, inv_cov and n_points are required");
+    if (!d->weights.ptr) {
+        if (!d->logits.ptr || !d->weights_scale.ptr) return fail(LC_E_NULL, "weights or (logits, weights_scale) are required");
+        if (d->logits.stride[3] != 1 || d->logits.stride[2] != d->W) return fail(LC_E_BADARG, "(H,W) planes must be contiguous");
+    }
+    const int rc = launch_select(*d, static_cast<cudaStream_t>(stream));
+    if (rc == -1) return fail(LC_E_BADARG, "sampled point count does not fit in shared memory");
+    return check_launch(rc);
+}
+
 }  // namespace lc
 
 extern "C" {
@@ -119,5 +140,6 @@ int lc_b200_pnp_jac_cov(const lc_args* a, void* stream) { return lc::dispatch_ja
 int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatch_jac(a, true, stream); }
 int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* stream) { return lc::dispatch_dense(a, stream); }
 int lc_b200_noc_bin_decode(const lc_decode_args* a, void* stream) { return lc::dispatch_decode(a, stream); }
+int lc_b200_dense_select(const lc_select_args* a, void* stream) { return lc::dispatch_select(a, stream); }
 
 }  // extern "C"

@@ -791,5 +791,6 @@ bool resident_supported(const lc_args& a, int mode);
 int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st);
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
 int launch_decode(const lc_decode_args& d, cudaStream_t st);
+int launch_select(const lc_select_args& d, cudaStream_t st);
 
 }  // namespace lc

@@ -307,3 +307,57 @@ def dense_pose_loss_noc_bin(bin_logits, raw_bits, msk_noc, logits, scale, noc_sc
     g_bin = np.zeros((B, C_, H, W))
     g_bin[sl] = g_bin_s
     return dict(loss=o["loss"], g_bin_logits=g_bin, g_logits=g_logits, g_scale=S, pts3d=pts3d)
+
+
+# ------------------------------------------------------------------------------------------------
+# Test-time point selection: test.py:67-119
+# ------------------------------------------------------------------------------------------------
+def _quantile_f32(vals, q):
+    """torch.quantile(vals (N,) fp32, q fp32 scalar), default 'linear' interpolation, restated in fp32:
+    rank = q*(N-1); lerp(sorted[floor], sorted[ceil], rank-floor) with torch's lerp (w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w))."""
+    f = np.float32
+    srt = np.sort(vals.astype(f))
+    rank = f(q) * f(len(srt) - 1)
+    lo = np.floor(rank)
+    w = f(rank - lo)
+    a, b = srt[int(lo)], srt[min(int(np.ceil(rank)), len(srt) - 1)]
+    d = f(b - a)
+    return f(a + f(w * d)) if w < f(0.5) else f(b - f(d * f(f(1) - w)))
+
+
+def dense_point_select(xyz, weights, msk_vis_logits, sample, mode, quantile=0.2, seg_thresh=0.5):
+    """CPU restatement (numpy, fp32 where the comparison outcome depends on it) of the selection in test.solve_pnp_dense:
+      test.py:70      seg_msk = sigmoid(msk_vis_logits) > seg_thresh
+      losses.py:142-161 (top_left=(0,0)): strided sub-sample of the gen_uv grid / weights / xyz / mask
+      test.py:95      den_inv_cov2d = den_inv_std2d ** 2
+      test.py:97-104  dense_point_select = 'mask' | 'quantile' | 'quantile_in_mask' (test.py:36-45 quantile_msk)
+      test.py:106     valid_index_lst = [v.nonzero()[:,0] ...]  (ordered indices)
+    xyz (B,H,W,3), weights (B,2,H,W) = softmax * scale, msk_vis_logits (B,1,H,W).
+    Returns dict(valid (B,N) bool, pts3d (B,N,3), pts2d (N,2), inv_std (B,N,2), inv_cov (B,N,2), thr (B,))."""
+    f = np.float32
+    xyz, weights, ml = np.asarray(xyz, f), np.asarray(weights, f), np.asarray(msk_vis_logits, f)
+    B, H, W, _ = xyz.shape
+    seg = (f(1) / (f(1) + np.exp(-ml[:, 0]).astype(f))) > f(seg_thresh)
+    ys, xs = np.meshgrid(np.arange(H, dtype=f), np.arange(W, dtype=f), indexing="ij")
+    pts2d = np.stack((xs[::sample, ::sample].reshape(-1), ys[::sample, ::sample].reshape(-1)), -1)
+    inv_std = weights[:, :, ::sample, ::sample].reshape(B, 2, -1).transpose(0, 2, 1)
+    pts3d = xyz[:, ::sample, ::sample].reshape(B, -1, 3)
+    m = seg[:, ::sample, ::sample].reshape(B, -1)
+    N = m.shape[1]
+    thr = np.zeros(B, f)
+    if mode == "mask":
+        valid = m.copy()
+    elif mode == "quantile":
+        wsum = (inv_std[..., 0] + inv_std[..., 1]).astype(f)
+        thr = np.array([_quantile_f32(wsum[b], quantile) for b in range(B)], f)
+        valid = wsum >= thr[:, None]
+    elif mode == "quantile_in_mask":
+        vis_ratio = (m.astype(f).sum(1, dtype=f) / f(N)).astype(f)       # seg_valid_mask.float().mean(-1)
+        qb = (f(1) - (f(1 - quantile) * vis_ratio).astype(f)).astype(f)  # 1 - (1-cfg.quantile) * vis_ratio
+        mf = m.astype(f)
+        wsum = ((inv_std[..., 0] * mf).astype(f) + (inv_std[..., 1] * mf).astype(f)).astype(f)
+        thr = np.array([_quantile_f32(wsum[b], qb[b]) for b in range(B)], f)
+        valid = (wsum >= thr[:, None]) & m
+    else:
+        raise ValueError(mode)
+    return dict(valid=valid, pts3d=pts3d, pts2d=pts2d, inv_std=inv_std, inv_cov=(inv_std * inv_std).astype(f), thr=thr)

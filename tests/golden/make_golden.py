@@ -195,14 +195,58 @@ def make_zebra():
         print(name, loss.detach().numpy(), os.path.getsize(path) // 1024, "KiB")
 
 
+def make_select():
+    """Test-time point selection of solve_pnp_dense (test.py:67-106).  test.py itself cannot be imported (mmcv), so its
+    quantile_msk (test.py:36-45) is exec'd from the unmodified source text and the glue lines around it are replayed with
+    the reference's own dense_pnp_matching_from_xyz / nn_out_to_xyz, in fp32 like the reference runs them."""
+    import re
+    import losses as ref_losses  # noqa: E402  (reference)
+    from torch import Tensor  # noqa: F401  (used by the exec'd source)
+    from typing import Union  # noqa: F401
+    src = open("/root/reference/test.py").read()
+    fn_src = re.search(r"^def quantile_msk\(.*?(?=^\S)", src, flags=re.S | re.M).group(0)
+    ns = dict(torch=torch, Tensor=torch.Tensor, Union=Union)
+    exec(fn_src, ns)
+    quantile_msk = ns["quantile_msk"]
+    from lc_b200.synth import make_dense_outputs
+    for name, B, H, W, sample, seed, scale_dim in (("select_b3_32x32_s1", 3, 32, 32, 1, 21, 1), ("select_b2_64x48_s2", 2, 64, 48, 2, 22, 2)):
+        d = make_dense_outputs(B, H, W, seed)
+        g = torch.Generator().manual_seed(seed)
+        msk_logits = 2.0 * torch.randn(B, 1, H, W, generator=g) + 0.8
+        scale = d["scale"] if scale_dim == 1 else d["scale"].expand(B, 2, 1, 1) * torch.tensor([1.0, 0.7]).reshape(1, 2, 1, 1)
+        lg = d["logits"]
+        with torch.no_grad():
+            seg_msk = torch.sigmoid(msk_logits) > 0.5                                                    # test.py:70
+            xyz_out = ref_losses.nn_out_to_xyz(d["xyz_noc"], d["noc_scale"], bit_cnt=None, inference=True)  # test.py:78-82
+            w_raw = lg.reshape(lg.shape[:-3] + (scale.shape[-3], -1)).softmax(dim=-1)                    # test.py:86-88
+            weights = w_raw.reshape_as(lg) * scale
+            p2, inv_std, p3, seg_valid = ref_losses.dense_pnp_matching_from_xyz(xyz_out.permute(0, 3, 1, 2), weights, seg_msk.squeeze(-3),
+                                                                               None, sample, top_left=(0, 0))   # test.py:91-93
+            out = dict(in_xyz_noc=d["xyz_noc"].numpy(), in_noc_scale=d["noc_scale"].numpy(), in_logits=lg.numpy(), in_scale=scale.numpy(),
+                       in_msk_logits=msk_logits.numpy(), sample=np.array(sample), ref_weights=weights.numpy(),
+                       ref_pts3d=p3.numpy(), ref_pts2d=p2.numpy(), ref_inv_cov=(inv_std ** 2).numpy())
+            out["valid_mask"] = seg_valid.numpy()                                                        # test.py:97-98
+            out["valid_quantile"] = quantile_msk(inv_std, 0.2).numpy()                                   # test.py:99-100
+            vis_ratio = seg_valid.float().mean(dim=-1)                                                   # test.py:101-104
+            quantile = 1 - (1 - 0.2) * vis_ratio
+            out["valid_quantile_in_mask"] = (quantile_msk(inv_std * seg_valid[..., None], quantile) * seg_valid).numpy()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, {k: int(out[k].sum()) for k in out if k.startswith("valid_")}, os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     if "--only-zebra" in sys.argv:
         make_zebra()
         return
+    if "--only-select" in sys.argv:
+        make_select()
+        return
     make_jac_exact()
     make_dense()
     make_zebra()
+    make_select()
     for name, B, N, seed, vmode, regime, store_jac in CASES:
         d = build_inputs(B, N, seed, vmode, regime)
         o = run_reference(d)

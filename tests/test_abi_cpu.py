@@ -43,18 +43,20 @@ def test_struct_layout_matches_header(tmp_path):
 
 def test_dense_struct_layout_matches_header(tmp_path):
     c = tmp_path / "sz.c"
-    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu",'
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu",'
                  'sizeof(lc_dense_args),offsetof(lc_dense_args,xyz_noc),offsetof(lc_dense_args,loss),'
                  'offsetof(lc_dense_args,loss_sum),offsetof(lc_dense_args,noc_bin_logits),offsetof(lc_dense_args,g_noc_bin),'
                  'offsetof(lc_dense_args,bit_cnt),offsetof(lc_dense_args,black_background),'
-                 'sizeof(lc_decode_args),offsetof(lc_decode_args,xyz));return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
+                 'sizeof(lc_decode_args),offsetof(lc_decode_args,xyz),sizeof(lc_select_args),offsetof(lc_select_args,xyz),'
+                 'offsetof(lc_select_args,n_points));return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
     exe = tmp_path / "sz"
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([gcc, "-o", str(exe), str(c)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    A, D = nat.lc_dense_args, nat.lc_decode_args
+    A, D, S = nat.lc_dense_args, nat.lc_decode_args, nat.lc_select_args
     assert got == [ctypes.sizeof(A), A.xyz_noc.offset, A.loss.offset, A.loss_sum.offset, A.noc_bin_logits.offset, A.g_noc_bin.offset,
-                   A.bit_cnt.offset, A.black_background.offset, ctypes.sizeof(D), D.xyz.offset]
+                   A.bit_cnt.offset, A.black_background.offset, ctypes.sizeof(D), D.xyz.offset, ctypes.sizeof(S), S.xyz.offset,
+                   S.n_points.offset]
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

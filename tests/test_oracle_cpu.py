@@ -145,3 +145,18 @@ def test_zebra_producer_oracle_matches_reference_golden(oracle, name):
     assert np.abs(noc - z["ref_noc_inference"]).max() <= 1e-7             # stored as fp32
     mod, raw = oracle.noc_to_bits(z["ref_noc_inference"].astype(np.float64), z["bit_cnt"])
     assert np.array_equal(np.packbits(mod), z["ref_target_mod"]) and np.array_equal(np.packbits(raw), z["ref_target_raw"])
+
+
+@pytest.mark.parametrize("name", ["select_b3_32x32_s1.npz", "select_b2_64x48_s2.npz"])
+def test_selection_oracle_matches_reference_golden(oracle, name):
+    """oracle.dense_point_select == the reference's quantile_msk / dense_pnp_matching_from_xyz / nn_out_to_xyz (test.py:36-45,
+    67-106) bit for bit: selected sets for the three cfg.dense_point_select rules and the gathered fp32 values."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    xyz = (z["in_xyz_noc"].transpose(0, 2, 3, 1) * z["in_noc_scale"][:, None, None, :]).astype(np.float32)
+    for mode in ("mask", "quantile", "quantile_in_mask"):
+        r = oracle.dense_point_select(xyz, z["ref_weights"], z["in_msk_logits"], int(z["sample"]), mode)
+        assert np.array_equal(r["valid"], z["valid_" + mode])
+        assert np.array_equal(r["pts3d"], z["ref_pts3d"]) and np.array_equal(r["inv_cov"], z["ref_inv_cov"])
+        assert np.array_equal(r["pts2d"], z["ref_pts2d"][0])
