@@ -218,6 +218,40 @@ typedef struct lc_select_args {
 
 int lc_b200_dense_select(const lc_select_args* a, void* cuda_stream);
 
+/*
+ * Pose-error metrics ("next" row f4): compute_pose_errors (lib/utils/evaluate.py:333-339) = error6d.add / adi / re / te
+ * (lib/utils/error6d.py:87-159) for a batch of poses, one CTA per pose (the reference: numpy + scipy cKDTree in a
+ * multiprocessing.Pool(6), evaluate.py:193-210).  All arrays fp64 like the reference's numpy code.
+ */
+typedef struct lc_eval_args {
+    int32_t abi_version, B, M, reserved0; /* M = model points per pose when pts_count is NULL */
+    lc_view R_est, t_est, R_gt, t_gt;     /* (B,3,3), (B,3), (B,3,3), (B,3) fp64 */
+    lc_view pts;                          /* (P,3) fp64 model points, strides [point, component] */
+    const int64_t* pts_offset;            /* (B) first model point of pose b in pts, or NULL (= 0) */
+    const int32_t* pts_count;             /* (B) model points of pose b, or NULL (= M) */
+    lc_view add, adi, re, te;             /* out (B) fp64, each may be NULL */
+} lc_eval_args;
+
+int lc_b200_pose_errors(const lc_eval_args* a, void* cuda_stream);
+
+/*
+ * Symmetric pose-candidate selection ("next" row f4): symmetry.select_pose_2d (mode 0, symmetry.py:8-31) and
+ * select_pose_3d (mode 1, symmetry.py:33-56): per sample the candidate (of Kc) with the smallest mean error; fp32.
+ */
+typedef struct lc_candi_args {
+    int32_t abi_version, B, N, Kc;
+    int32_t mode, reserved0;   /* 0: 2-D reprojection error, 1: 3-D back-projection error */
+    lc_view K;                 /* (B,3,3) */
+    lc_view pts_a;             /* mode 0: pts3d (B,N,3); mode 1: pts3d_out (B,N,3) */
+    lc_view pts_b;             /* mode 0: pts2d (B,N,2); mode 1: homo_z (B,N,3) */
+    lc_view candi;             /* (B,Kc,3,4) */
+    lc_view best;              /* out (B,3,4) or NULL */
+    lc_view err;               /* out (B,Kc) mean error per candidate, or NULL */
+    int32_t* best_index;       /* out (B) or NULL */
+} lc_candi_args;
+
+int lc_b200_select_pose(const lc_candi_args* a, void* cuda_stream);
+
 int lc_b200_abi_version(void);
 const char* lc_b200_last_error(void);
 

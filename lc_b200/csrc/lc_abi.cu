@@ -125,6 +125,26 @@ static int dispatch_select(const lc_select_args* d, void* stream) {
     return check_launch(rc);
 }
 
+static int dispatch_eval(const lc_eval_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->M < 0) return fail(LC_E_BADARG, "B and M must be non-negative");
+    if (d->B == 0) return LC_OK;
+    if (!d->R_est.ptr || !d->t_est.ptr || !d->R_gt.ptr || !d->t_gt.ptr || !d->pts.ptr) return fail(LC_E_NULL, "R_est, t_est, R_gt, t_gt and pts are required");
+    return check_launch(launch_pose_errors(*d, static_cast<cudaStream_t>(stream)));
+}
+
+static int dispatch_candi(const lc_candi_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->N <= 0 || d->Kc <= 0 || (d->mode != 0 && d->mode != 1)) return fail(LC_E_BADARG, "bad B / N / Kc / mode");
+    if (d->B == 0) return LC_OK;
+    if (!d->K.ptr || !d->pts_a.ptr || !d->pts_b.ptr || !d->candi.ptr) return fail(LC_E_NULL, "K, pts_a, pts_b and candi are required");
+    return check_launch(launch_select_pose(*d, static_cast<cudaStream_t>(stream)));
+}
+
 }  // namespace lc
 
 extern "C" {
@@ -141,5 +161,7 @@ int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatc
 int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* stream) { return lc::dispatch_dense(a, stream); }
 int lc_b200_noc_bin_decode(const lc_decode_args* a, void* stream) { return lc::dispatch_decode(a, stream); }
 int lc_b200_dense_select(const lc_select_args* a, void* stream) { return lc::dispatch_select(a, stream); }
+int lc_b200_pose_errors(const lc_eval_args* a, void* stream) { return lc::dispatch_eval(a, stream); }
+int lc_b200_select_pose(const lc_candi_args* a, void* stream) { return lc::dispatch_candi(a, stream); }
 
 }  // extern "C"

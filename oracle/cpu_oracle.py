@@ -361,3 +361,44 @@ def dense_point_select(xyz, weights, msk_vis_logits, sample, mode, quantile=0.2,
     else:
         raise ValueError(mode)
     return dict(valid=valid, pts3d=pts3d, pts2d=pts2d, inv_std=inv_std, inv_cov=(inv_std * inv_std).astype(f), thr=thr)
+
+
+# ------------------------------------------------------------------------------------------------
+# Pose-error metrics and symmetric candidate selection
+# ------------------------------------------------------------------------------------------------
+def pose_errors(R_est, t_est, R_gt, t_gt, pts):
+    """lib/utils/evaluate.py:333-339 compute_pose_errors for a batch: error6d.add (:87-101), adi (:104-124, nearest neighbour by
+    brute force instead of cKDTree), re (:127-140, degrees), te (:143-152).  fp64."""
+    R_est, t_est, R_gt, t_gt, pts = (np.asarray(v, np.float64) for v in (R_est, t_est, R_gt, t_gt, pts))
+    B = len(R_est)
+    out = {k: np.zeros(B) for k in ("adi", "add", "re", "te")}
+    for b in range(B):
+        pe = pts @ R_est[b].T + t_est[b].reshape(1, 3)
+        pg = pts @ R_gt[b].T + t_gt[b].reshape(1, 3)
+        out["add"][b] = np.linalg.norm(pe - pg, axis=1).mean()
+        nn = np.empty(len(pts))
+        for j0 in range(0, len(pts), 512):
+            d2 = ((pg[j0:j0 + 512, None, :] - pe[None, :, :]) ** 2).sum(-1)
+            nn[j0:j0 + 512] = np.sqrt(d2.min(1))
+        out["adi"][b] = nn.mean()
+        cs = min(1.0, max(-1.0, 0.5 * (np.trace(R_est[b] @ np.linalg.inv(R_gt[b])) - 1.0)))
+        out["re"][b] = 180.0 * np.arccos(cs) / np.pi
+        out["te"][b] = np.linalg.norm(t_gt[b].reshape(3) - t_est[b].reshape(3))
+    return out
+
+
+def select_pose(mode, cam_K, pts_a, pts_b, pose_candi):
+    """symmetry.py:8-31 select_pose_2d (mode 0: pts_a = pts3d, pts_b = pts2d) / :33-56 select_pose_3d (mode 1: pts_a = pts3d_out,
+    pts_b = homo_z).  Returns (best (B,3,4), index (B,), err (B,K)), fp64 arithmetic."""
+    K, A, Bp, C_ = (np.asarray(v, np.float64) for v in (cam_K, pts_a, pts_b, pose_candi))
+    R, t = C_[..., :3, :3], C_[..., :3, 3]
+    if mode == 0:
+        x = np.einsum("bkij,bnj->bkni", R, A) + t[:, :, None, :]
+        h = np.einsum("bij,bknj->bkni", K, x)
+        err = np.linalg.norm(h[..., :2] / h[..., 2:3] - Bp[:, None], axis=-1).mean(-1)
+    else:
+        cam = np.einsum("bij,bnj->bni", np.linalg.inv(K), Bp)
+        ref = np.einsum("bkji,bknj->bkni", R, cam[:, None] - t[:, :, None, :])
+        err = np.linalg.norm(A[:, None] - ref, axis=-1).mean(-1)
+    idx = err.argmin(1)
+    return C_[np.arange(len(idx)), idx], idx, err

@@ -235,8 +235,53 @@ def make_select():
         print(name, {k: int(out[k].sum()) for k in out if k.startswith("valid_")}, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_eval():
+    """compute_pose_errors (lib/utils/error6d.py add/adi/re/te) and symmetry.select_pose_2d/3d, run unmodified."""
+    from lib.utils import error6d  # noqa: E402  (reference)
+    import symmetry as ref_sym      # noqa: E402  (reference)
+    from lc_b200.synth import make_correspondences, quat_to_matrix
+    rng = np.random.default_rng(7)
+    B, M = 6, 2500
+    pts = rng.uniform(-1, 1, (M, 3)) * np.array([40.0, 55.0, 70.0])
+    c = make_correspondences(B, 4, 31)
+    R_gt = quat_to_matrix(c.pose[:, :4]).numpy()
+    t_gt = c.pose[:, 4:].numpy()
+    R_est = quat_to_matrix(c.start[:, :4]).numpy()
+    t_est = c.start[:, 4:].numpy()
+    R_est[3] = R_gt[3] @ np.diag([-1.0, -1.0, 1.0])            # a 180 degree flip: ADI << ADD
+    R_est[4], t_est[4] = R_gt[4], t_gt[4]                        # exact pose: all errors 0
+    errs = {k: np.zeros(B) for k in ("adi", "add", "re", "te")}
+    for b in range(B):
+        errs["adi"][b] = error6d.adi(R_est[b], t_est[b].reshape(3, 1), R_gt[b], t_gt[b].reshape(3, 1), pts)
+        errs["add"][b] = error6d.add(R_est[b], t_est[b].reshape(3, 1), R_gt[b], t_gt[b].reshape(3, 1), pts)
+        errs["re"][b] = error6d.re(R_est[b], R_gt[b])
+        errs["te"][b] = error6d.te(t_est[b], t_gt[b])
+    # candidate selection: Kc candidates = the true pose composed with rotations about z, listed from a random offset
+    Bc, N, Kc = 4, 300, 12
+    cc = make_correspondences(Bc, N, 33).to(torch.float32)
+    Rt = quat_to_matrix(cc.pose[:, :4].double()).float()
+    ang = torch.arange(Kc, dtype=torch.float32) * (2 * np.pi / Kc)
+    Rz = torch.zeros(Kc, 3, 3)
+    Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1], Rz[:, 2, 2] = torch.cos(ang), -torch.sin(ang), torch.sin(ang), torch.cos(ang), 1
+    shift = torch.tensor([0, 5, 7, 11])
+    candi = torch.stack([torch.cat((Rt[b] @ Rz.roll(int(shift[b]), 0), cc.pose[b, 4:].float().reshape(1, 3, 1).expand(Kc, 3, 1)), -1) for b in range(Bc)])
+    P = cc.pts3d @ Rt.mT + cc.pose[:, None, 4:].float()
+    homo_z = P @ cc.K.mT
+    noisy3d = cc.pts3d + 0.5 * torch.randn(cc.pts3d.shape, generator=torch.Generator().manual_seed(3))
+    best2d = ref_sym.select_pose_2d(cc.K, cc.pts3d, cc.pts2d, candi)
+    best3d = ref_sym.select_pose_3d(cc.K, noisy3d, homo_z, candi)
+    path = os.path.join(HERE, "eval_b6_m2500.npz")
+    np.savez_compressed(path, pts=pts, R_est=R_est, t_est=t_est, R_gt=R_gt, t_gt=t_gt, **{"ref_" + k: v for k, v in errs.items()},
+                        c_K=cc.K.numpy(), c_pts3d=cc.pts3d.numpy(), c_pts2d=cc.pts2d.numpy(), c_noisy3d=noisy3d.numpy(),
+                        c_homo_z=homo_z.numpy(), c_candi=candi.numpy(), ref_best2d=best2d.numpy(), ref_best3d=best3d.numpy())
+    print("eval_b6_m2500", errs, os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if "--only-eval" in sys.argv:
+        make_eval()
+        return
     if "--only-zebra" in sys.argv:
         make_zebra()
         return
@@ -247,6 +292,7 @@ def main():
     make_dense()
     make_zebra()
     make_select()
+    make_eval()
     for name, B, N, seed, vmode, regime, store_jac in CASES:
         d = build_inputs(B, N, seed, vmode, regime)
         o = run_reference(d)

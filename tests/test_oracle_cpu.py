@@ -160,3 +160,18 @@ def test_selection_oracle_matches_reference_golden(oracle, name):
         assert np.array_equal(r["valid"], z["valid_" + mode])
         assert np.array_equal(r["pts3d"], z["ref_pts3d"]) and np.array_equal(r["inv_cov"], z["ref_inv_cov"])
         assert np.array_equal(r["pts2d"], z["ref_pts2d"][0])
+
+
+def test_eval_oracle_matches_reference_golden(oracle):
+    """oracle.pose_errors / select_pose == error6d.add/adi/re/te (numpy + cKDTree) and symmetry.select_pose_2d/3d."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "eval_b6_m2500.npz"))
+    o = oracle.pose_errors(z["R_est"], z["t_est"], z["R_gt"], z["t_gt"], z["pts"])
+    for k in ("adi", "add", "te"):
+        assert np.allclose(o[k], z["ref_" + k], rtol=1e-12, atol=1e-12), k
+    assert np.allclose(o["re"], z["ref_re"], rtol=0, atol=1e-5)          # acos near 1 amplifies rounding (1e-16 -> 1e-6 deg)
+    b2, i2, _ = oracle.select_pose(0, z["c_K"], z["c_pts3d"], z["c_pts2d"], z["c_candi"])
+    b3, i3, _ = oracle.select_pose(1, z["c_K"], z["c_noisy3d"], z["c_homo_z"], z["c_candi"])
+    assert np.array_equal(b2.astype(np.float32), z["ref_best2d"]) and np.array_equal(b3.astype(np.float32), z["ref_best3d"])
+    assert list(i2) == [0, 5, 7, 11] and list(i3) == [0, 5, 7, 11]       # the candidate lists were rolled by [0, 5, 7, 11] of 12
