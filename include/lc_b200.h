@@ -219,6 +219,28 @@ typedef struct lc_select_args {
 int lc_b200_dense_select(const lc_select_args* a, void* cuda_stream);
 
 /*
+ * Device-side pose initialiser ("next" row f2): the role of lib/pnp/cv2_solver.solve (cv2_solver.py:6-88,
+ * cv2.solvePnPRansac(EPNP, 150 iterations) per sample on the host) in test.solve_pnp / solve_pnp_dense (test.py:60, 120):
+ * a start pose for the weighted LM solve and an inlier set for the 'weighted_filtered' branch (test.py:131-134).
+ * Weighted DLT reduced to a 4x4 eigenproblem + Cauchy IRLS on the pixel reprojection error; NOT OpenCV's RANSAC (see
+ * lc_init.cu).  fp32 arrays, fp64 arithmetic.
+ */
+typedef struct lc_init_args {
+    int32_t abi_version, B, N, irls_rounds; /* irls_rounds: robust re-solves after the first (3) */
+    float reproj_thresh, reserved0;         /* pixels: cv2 reprojectionError (Cauchy scale and inlier threshold) */
+    lc_view K, pts3d, pts2d;                /* (B,3,3), (B,N,3), (B,N,2) */
+    lc_view weights;                        /* (B,N,2) inverse variances (base weights) or NULL (= 1) */
+    lc_view reproj_thresh_b;                /* (B) per-sample threshold (cfg.rel_reproj_err, test.py:115-117) or NULL */
+    const int32_t* n_points;                /* (B) or NULL */
+    lc_view state;                          /* out (B,7) wxyz + t */
+    int32_t* invalid;                       /* out (B) or NULL: fewer than 6 points / degenerate system */
+    uint8_t* inlier;                        /* out (B,N) or NULL: reprojection error < threshold under the returned pose */
+    int32_t* n_inliers;                     /* out (B) or NULL */
+} lc_init_args;
+
+int lc_b200_pnp_init(const lc_init_args* a, void* cuda_stream);
+
+/*
  * Pose-error metrics ("next" row f4): compute_pose_errors (lib/utils/evaluate.py:333-339) = error6d.add / adi / re / te
  * (lib/utils/error6d.py:87-159) for a batch of poses, one CTA per pose (the reference: numpy + scipy cKDTree in a
  * multiprocessing.Pool(6), evaluate.py:193-210).  All arrays fp64 like the reference's numpy code.

@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("LC_B200_LIB") or os.path.join(_HERE, "liblc_b200.so")   # env override: instrumented builds (tools/)
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu", "lc_select.cu", "lc_eval.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu", "lc_select.cu", "lc_eval.cu", "lc_init.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "csrc", "lc_pose.cuh"),
            os.path.join(_HERE, "csrc", "lc_resident.cuh"),
            os.path.join(_ROOT, "include", "lc_b200.h")]
@@ -32,7 +32,7 @@ ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
            "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd",
            "lc_b200_dense_loss_fwd_bwd", "lc_b200_noc_bin_decode", "lc_b200_dense_select", "lc_b200_pose_errors",
-           "lc_b200_select_pose")
+           "lc_b200_select_pose", "lc_b200_pnp_init")
 
 
 class NativeLibraryError(RuntimeError):
@@ -97,6 +97,14 @@ class lc_select_args(C.Structure):
                 + [("index", C.c_void_p), ("n_points", C.c_void_p)])
 
 
+class lc_init_args(C.Structure):
+    _fields_ = ([("abi_version", C.c_int32), ("B", C.c_int32), ("N", C.c_int32), ("irls_rounds", C.c_int32),
+                 ("reproj_thresh", C.c_float), ("reserved0", C.c_float)]
+                + [(f, lc_view) for f in ("K", "pts3d", "pts2d", "weights", "reproj_thresh_b")]
+                + [("n_points", C.c_void_p), ("state", lc_view), ("invalid", C.c_void_p), ("inlier", C.c_void_p),
+                   ("n_inliers", C.c_void_p)])
+
+
 class lc_eval_args(C.Structure):
     _fields_ = ([("abi_version", C.c_int32), ("B", C.c_int32), ("M", C.c_int32), ("reserved0", C.c_int32)]
                 + [(f, lc_view) for f in ("R_est", "t_est", "R_gt", "t_gt", "pts")]
@@ -159,7 +167,7 @@ def lib() -> C.CDLL:
         for name in EXPORTS[3:]:
             argt = {"lc_b200_dense_loss_fwd_bwd": lc_dense_args, "lc_b200_noc_bin_decode": lc_decode_args,
                     "lc_b200_dense_select": lc_select_args, "lc_b200_pose_errors": lc_eval_args,
-                    "lc_b200_select_pose": lc_candi_args}.get(name, lc_args)
+                    "lc_b200_select_pose": lc_candi_args, "lc_b200_pnp_init": lc_init_args}.get(name, lc_args)
             getattr(handle, name).argtypes = [C.POINTER(argt), C.c_void_p]
             getattr(handle, name).restype = C.c_int
         if handle.lc_b200_abi_version() != ABI_VERSION:

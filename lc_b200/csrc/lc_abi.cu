@@ -125,6 +125,17 @@ static int dispatch_select(const lc_select_args* d, void* stream) {
     return check_launch(rc);
 }
 
+static int dispatch_init(const lc_init_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->N < 0 || d->irls_rounds < 0 || d->irls_rounds > 16) return fail(LC_E_BADARG, "bad B / N / irls_rounds");
+    if (d->B == 0) return LC_OK;
+    if (!d->K.ptr || !d->pts3d.ptr || !d->pts2d.ptr || !d->state.ptr) return fail(LC_E_NULL, "K, pts3d, pts2d and state are required");
+    if (!d->reproj_thresh_b.ptr && !(d->reproj_thresh > 0.f)) return fail(LC_E_BADARG, "reproj_thresh must be positive");
+    return check_launch(launch_init(*d, static_cast<cudaStream_t>(stream)));
+}
+
 static int dispatch_eval(const lc_eval_args* d, void* stream) {
     g_launches = 0;
     if (!d) return fail(LC_E_NULL, "args is NULL");
@@ -161,6 +172,7 @@ int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatc
 int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* stream) { return lc::dispatch_dense(a, stream); }
 int lc_b200_noc_bin_decode(const lc_decode_args* a, void* stream) { return lc::dispatch_decode(a, stream); }
 int lc_b200_dense_select(const lc_select_args* a, void* stream) { return lc::dispatch_select(a, stream); }
+int lc_b200_pnp_init(const lc_init_args* a, void* stream) { return lc::dispatch_init(a, stream); }
 int lc_b200_pose_errors(const lc_eval_args* a, void* stream) { return lc::dispatch_eval(a, stream); }
 int lc_b200_select_pose(const lc_candi_args* a, void* stream) { return lc::dispatch_candi(a, stream); }
 

@@ -792,6 +792,7 @@ int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st);
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
 int launch_decode(const lc_decode_args& d, cudaStream_t st);
 int launch_select(const lc_select_args& d, cudaStream_t st);
+int launch_init(const lc_init_args& d, cudaStream_t st);
 int launch_pose_errors(const lc_eval_args& d, cudaStream_t st);
 int launch_select_pose(const lc_candi_args& d, cudaStream_t st);
 

@@ -402,3 +402,67 @@ def select_pose(mode, cam_K, pts_a, pts_b, pose_candi):
         err = np.linalg.norm(A[:, None] - ref, axis=-1).mean(-1)
     idx = err.argmin(1)
     return C_[np.arange(len(idx)), idx], idx, err
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-side initialiser: numpy restatement of lc_init.cu (our algorithm; the reference uses OpenCV)
+# ------------------------------------------------------------------------------------------------
+def pnp_init(K, pts3d, pts2d, weights=None, reproj_thresh=3.0, irls_rounds=3):
+    """Weighted DLT reduced to a 4x4 eigenproblem + Cauchy IRLS, one pose.  K (3,3), pts3d (n,3), pts2d (n,2), weights (n,2)
+    inverse variances or None.  Returns (ok, R (3,3), t (3,), inlier (n,) bool).  Same steps and formulas as lc_init.cu."""
+    K, X, x = np.asarray(K, np.float64), np.asarray(pts3d, np.float64), np.asarray(pts2d, np.float64)
+    n = len(X)
+    if n < 6:
+        return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+    base = np.ones(n) if weights is None else 0.5 * np.asarray(weights, np.float64).sum(1)
+    base = np.where((base > 0) & np.isfinite(base), base, 0.0)
+    Ki = np.linalg.inv(K)
+    cen = X.mean(0)
+    var = (X * X).mean(0) - cen * cen
+    sc = np.sqrt(var.sum() / 3.0) if var.sum() > 0 else 1.0
+    Y = np.concatenate(((X - cen) / sc, np.ones((n, 1))), 1)
+    h = np.concatenate((x, np.ones((n, 1))), 1) @ Ki.T
+    xh, yh = h[:, 0] / h[:, 2], h[:, 1] / h[:, 2]
+    R, t = np.eye(3), np.zeros(3)
+
+    def reproj_err2(R, t):
+        P = X @ R.T + t
+        hh = P @ K.T
+        e = hh[:, :2] / hh[:, 2:3] - x
+        return (e * e).sum(1), hh[:, 2]
+
+    for rnd in range(irls_rounds + 1):
+        wt = base.copy()
+        if rnd > 0:
+            e2, h2 = reproj_err2(R, t)
+            e2 = e2 / reproj_thresh ** 2
+            wt = wt * np.where((h2 > 0) & np.isfinite(e2), 1.0 / (1.0 + e2), 0.0)
+        YY = Y[:, :, None] * Y[:, None, :]
+        S = (wt[:, None, None] * YY).sum(0)
+        Sx = ((wt * xh)[:, None, None] * YY).sum(0)
+        Sy = ((wt * yh)[:, None, None] * YY).sum(0)
+        Sq = ((wt * (xh * xh + yh * yh))[:, None, None] * YY).sum(0)
+        try:
+            np.linalg.cholesky(S)
+        except np.linalg.LinAlgError:
+            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+        Zx, Zy = np.linalg.solve(S, Sx), np.linalg.solve(S, Sy)
+        D = Sq - Sx @ Zx - Sy @ Zy
+        D = 0.5 * (D + D.T)
+        ev, V = np.linalg.eigh(D)
+        p3 = V[:, 0]
+        P = np.stack((Zx @ p3, Zy @ p3, p3))
+        Q = np.concatenate((P[:, :3] / sc, (P[:, 3] - P[:, :3] @ cen / sc)[:, None]), 1)
+        if Q[2, :3] @ cen + Q[2, 3] < 0:
+            Q = -Q
+        n1, n2 = np.linalg.norm(Q[0, :3]), np.linalg.norm(Q[1, :3])
+        lam = 0.5 * (n1 + n2)
+        r1 = Q[0, :3] / n1
+        r2 = Q[1, :3] - (r1 @ Q[1, :3]) * r1
+        r2 = r2 / np.linalg.norm(r2)
+        R = np.stack((r1, r2, np.cross(r1, r2)))
+        t = Q[:, 3] / lam
+        if not (np.isfinite(R).all() and np.isfinite(t).all() and lam > 0):
+            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+    e2, h2 = reproj_err2(R, t)
+    return True, R, t, (h2 > 0) & (e2 < reproj_thresh ** 2)

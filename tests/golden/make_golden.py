@@ -277,8 +277,45 @@ def make_eval():
     print("eval_b6_m2500", errs, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_init():
+    """Start poses and inlier sets of the reference's cv2_solver.solve (cv2_solver.py:6-88: cv2.solvePnPRansac, EPNP, 150
+    iterations), run unmodified on synthetic correspondences with an axis-aligned K (OpenCV ignores the off-diagonal terms)."""
+    from lib.pnp import cv2_solver  # noqa: E402  (reference)
+    from lc_b200.synth import make_correspondences, quat_to_matrix
+    import cv2
+    cv2.setRNGSeed(1234)
+    out = {}
+    for tag, B, N, outl in (("a", 6, 256, 0.1), ("b", 6, 16, 0.0)):
+        c = make_correspondences(B, N, 41, outlier_frac=outl)
+        Rt = quat_to_matrix(c.pose[:, :4])
+        P = c.pts3d @ Rt.mT + c.pose[:, None, 4:]
+        h = P @ c.K.mT
+        noise = c.pts2d - h[..., :2] / h[..., 2:]
+        f = (c.K[:, 0, 0] ** 2 + c.K[:, 0, 1] ** 2).sqrt()
+        K0 = torch.zeros(B, 3, 3, dtype=torch.float64)
+        K0[:, 0, 0], K0[:, 1, 1], K0[:, 0, 2], K0[:, 1, 2], K0[:, 2, 2] = f, f, 32.0, 32.0, 1.0
+        h0 = P @ K0.mT
+        x0 = h0[..., :2] / h0[..., 2:] + noise
+        K32, X32, x32 = K0.float(), c.pts3d.float(), x0.float()
+        invalids, states, inliers = cv2_solver.solve(K32, X32, x32, reprojectionError=3.0)
+        mask = np.zeros((B, N), bool)
+        for b, idx in enumerate(inliers):
+            mask[b, idx.numpy()] = True
+        out.update({f"{tag}_K": K32.numpy(), f"{tag}_pts3d": X32.numpy(), f"{tag}_pts2d": x32.numpy(),
+                    f"{tag}_inv_std": c.inv_std.float().numpy(), f"{tag}_pose": c.pose.float().numpy(),
+                    f"{tag}_cv_states": torch.stack(states).float().numpy(), f"{tag}_cv_invalid": np.array(invalids),
+                    f"{tag}_cv_inliers": mask})
+        print(tag, "cv2 invalid", list(invalids), "inlier fraction", mask.mean(1).round(2))
+    path = os.path.join(HERE, "init_cv2.npz")
+    np.savez_compressed(path, **out)
+    print("init_cv2", os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
+    if "--only-init" in sys.argv:
+        make_init()
+        return
     if "--only-eval" in sys.argv:
         make_eval()
         return
@@ -293,6 +330,7 @@ def main():
     make_zebra()
     make_select()
     make_eval()
+    make_init()
     for name, B, N, seed, vmode, regime, store_jac in CASES:
         d = build_inputs(B, N, seed, vmode, regime)
         o = run_reference(d)

@@ -175,3 +175,31 @@ def test_eval_oracle_matches_reference_golden(oracle):
     b3, i3, _ = oracle.select_pose(1, z["c_K"], z["c_noisy3d"], z["c_homo_z"], z["c_candi"])
     assert np.array_equal(b2.astype(np.float32), z["ref_best2d"]) and np.array_equal(b3.astype(np.float32), z["ref_best3d"])
     assert list(i2) == [0, 5, 7, 11] and list(i3) == [0, 5, 7, 11]       # the candidate lists were rolled by [0, 5, 7, 11] of 12
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_init_oracle_lands_in_the_same_lm_basin_as_opencv(oracle, tag):
+    """The initialiser restated in oracle.pnp_init is our own algorithm (the reference calls OpenCV's RANSAC-EPnP).  What ties
+    it to the reference: the LM solve started from it stops at the same optimum as the LM solve started from the pose the
+    reference's cv2_solver.solve returned (fixture init_cv2.npz), within the solver's early-stop gap."""
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "init_cv2.npz"))
+    K, X, x, s = (z[f"{tag}_{k}"] for k in ("K", "pts3d", "pts2d", "inv_std"))
+    B = len(K)
+    from scipy.spatial.transform import Rotation as Ro
+    starts = np.zeros((B, 7), np.float32)
+    for b in range(B):
+        ok, R, t, inl = oracle.pnp_init(K[b], X[b], x[b], s[b] ** 2, 3.0, 3)
+        assert ok
+        q = Ro.from_matrix(R).as_quat()
+        starts[b] = np.concatenate(([q[3]], q[:3], t))
+        # the inlier sets agree with RANSAC's up to points near the 3 px threshold / a slightly different pose
+        assert (inl != z[f"{tag}_cv_inliers"][b]).mean() <= (0.15 if X.shape[1] >= 64 else 0.25)
+    L = np.zeros(X.shape[:2] + (2, 2), np.float32)
+    L[..., 0, 0], L[..., 1, 1] = s[..., 0], s[..., 1]
+    ours = oracle.lm_solve(K, X, x, L, starts)
+    cv = oracle.lm_solve(K, X, x, L, z[f"{tag}_cv_states"])
+    assert not ours["invalid"].any() and not cv["invalid"].any()
+    assert quat_angle(ours["states"][:, :4].astype(np.float64), cv["states"][:, :4].astype(np.float64)).max() <= 1e-3
+    assert (np.abs(ours["states"][:, 4:] - cv["states"][:, 4:]).max(1) <= 2e-3 * np.abs(cv["states"][:, 4:]).max(1)).all()
