@@ -62,16 +62,38 @@ def dense_point_select(xyz: Tensor, msk_vis_logits: Tensor, *, xyz_weight_logits
 
 
 def solve_pnp_dense(K: Tensor, xyz: Tensor, msk_vis_logits: Tensor, xyz_weight_logits: Tensor, xyz_weights_scale: Tensor,
-                    start: Tensor, *, noc_scale: Optional[Tensor] = None, sample: int = 2,
-                    dense_point_select: str = "quantile_in_mask", quantile: float = 0.2, seg_thresh: float = 0.5):
-    """Device-resident ``'weighted'`` branch of ``test.solve_pnp_dense`` (``test.py:67-129``) given a start pose ``(B,7)``
-    (the reference takes it from ``cv2_solver.solve``, EPnP-RANSAC on the host): selection launch + LM launch, no sync.
-    Returns ``(invalid_dict, states (B,7), selection)``."""
-    from .pnp import cer_solver
-    sel = dense_point_select_ = dense_point_select
-    sel = globals()["dense_point_select"](xyz, msk_vis_logits, xyz_weight_logits=xyz_weight_logits,
-                                          xyz_weights_scale=xyz_weights_scale, noc_scale=noc_scale, sample=sample,
-                                          dense_point_select=dense_point_select_, quantile=quantile, seg_thresh=seg_thresh)
-    invalid_dict, states = cer_solver.solve(K, sel["pts3d"], sel["pts2d"], sel["inv_cov"], start, sel["n_points"],
-                                            num_workers=4, filter_input_nan=True)       # test.py:127
-    return invalid_dict, states, sel
+                    start: Optional[Tensor] = None, *, noc_scale: Optional[Tensor] = None, sample: int = 2,
+                    dense_point_select: str = "quantile_in_mask", quantile: float = 0.2, seg_thresh: float = 0.5,
+                    solvers=("weighted",), reprojectionError=3.0):
+    """Device-resident ``test.solve_pnp_dense`` (``test.py:67-136``) after the network and the xyz decode:
+
+    selection launch (``:84-119``) -> start pose (``:120``; ``start=None`` uses ``lc_b200.pnp.init_solver`` in place of
+    ``cv2_solver.solve``) -> ``'weighted'`` LM solve on the selected points (``:125-128``) and/or ``'weighted_filtered'`` LM
+    solve on the initialiser's inliers (``:130-134``).  No device->host synchronisation anywhere.  The inlier restriction is
+    applied by zeroing the inverse variances of the other points: a point with zero weight adds nothing to the cost, the
+    Jacobian or the normal equations, so the solve equals the solve on the compacted inlier list.
+    Returns ``(dict name -> states (B,7), selection dict)`` with the reference's result names (``'weighted'``,
+    ``'weighted-filtered'``)."""
+    from .pnp import cer_solver, init_solver
+    sel = dense_point_select_fn(xyz, msk_vis_logits, xyz_weight_logits=xyz_weight_logits, xyz_weights_scale=xyz_weights_scale,
+                                noc_scale=noc_scale, sample=sample, dense_point_select=dense_point_select, quantile=quantile,
+                                seg_thresh=seg_thresh)
+    inliers = None
+    if start is None:
+        invalid0, start, inliers = init_solver.solve(K, sel["pts3d"], sel["pts2d"], weights=sel["inv_cov"], n_points=sel["n_points"],
+                                                     reprojectionError=reprojectionError)
+        sel["init_invalid"], sel["start"], sel["inliers"] = invalid0, start, inliers
+    res = {}
+    if "weighted" in solvers:
+        res["weighted"] = cer_solver.solve(K, sel["pts3d"], sel["pts2d"], sel["inv_cov"], start, sel["n_points"],
+                                           num_workers=4, filter_input_nan=True)[1]                       # test.py:127
+    if "weighted_filtered" in solvers:
+        if inliers is None:
+            raise ValueError("'weighted_filtered' needs the initialiser's inlier set: call with start=None")
+        icov_in = sel["inv_cov"] * inliers["mask"].unsqueeze(-1)
+        res["weighted-filtered"] = cer_solver.solve(K, sel["pts3d"], sel["pts2d"], icov_in, start, sel["n_points"],
+                                                    num_workers=4, filter_input_nan=True)[1]              # test.py:133
+    return res, sel
+
+
+dense_point_select_fn = dense_point_select

@@ -122,9 +122,9 @@ def test_selection_feeds_the_solver_without_a_host_sync(oracle):
     q0 = torch.stack((w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
                       w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2), -1)
     start = torch.cat((q0, d["pose"][:, 4:] * 1.01), -1)
-    inv, states, sel = solve_pnp_dense(d["K"], d["xyz_noc"].permute(0, 2, 3, 1), ml, d["logits"], d["scale"], start,
-                                       noc_scale=d["noc_scale"], sample=2, dense_point_select="quantile_in_mask")
-    assert not inv["invalids"].any()
+    res, sel = solve_pnp_dense(d["K"], d["xyz_noc"].permute(0, 2, 3, 1), ml, d["logits"], d["scale"], start,
+                               noc_scale=d["noc_scale"], sample=2, dense_point_select="quantile_in_mask")
+    states = res["weighted"]
     assert (sel["pts2d"][:, :, 1][sel["pts2d"][:, :, 1] > 0].min() >= 8)          # rows 0..7 are outside the mask
     st = states.cpu().numpy().astype(np.float64)
     assert quat_angle(st[:, :4], d["pose"][:, :4].cpu().numpy().astype(np.float64)).max() < 0.01   # start was 0.02 rad away
@@ -133,5 +133,31 @@ def test_selection_feeds_the_solver_without_a_host_sync(oracle):
         L = torch.diag_embed(sel["inv_cov"][b:b + 1, :n].sqrt()).cpu().numpy()
         o = oracle.lm_solve(d["K"][b:b + 1].cpu().numpy(), sel["pts3d"][b:b + 1, :n].cpu().numpy(), sel["pts2d"][b:b + 1, :n].cpu().numpy(),
                             L, start[b:b + 1].cpu().numpy())
+        assert quat_angle(st[b:b + 1, :4], o["states"][:, :4].astype(np.float64)).max() <= 1e-6
+        assert np.abs(st[b, 4:] - o["states"][0, 4:]).max() <= 1e-6 * np.abs(o["states"][0, 4:]).max()
+
+
+def test_full_test_time_chain_without_a_start_pose(oracle):
+    """selection -> device initialiser -> 'weighted' and 'weighted_filtered' LM solves (test.py:84-134), all on the device.
+    The filtered solve (weights of non-inliers zeroed) equals the CPU LM oracle run on the compacted inlier list."""
+    from lc_b200.select import solve_pnp_dense
+    from lc_b200.synth import make_dense_outputs
+    B, H, W = 3, 64, 64
+    d = {k: v.cuda() for k, v in make_dense_outputs(B, H, W, 9).items()}
+    ml = torch.full((B, 1, H, W), 3.0, device="cuda")
+    res, sel = solve_pnp_dense(d["K"], d["xyz_noc"].permute(0, 2, 3, 1), ml, d["logits"], d["scale"], None, noc_scale=d["noc_scale"],
+                               sample=2, dense_point_select="quantile_in_mask", solvers=("weighted", "weighted_filtered"))
+    assert not sel["init_invalid"].any()
+    truth = d["pose"][:, :4].cpu().numpy().astype(np.float64)
+    for name in ("weighted", "weighted-filtered"):
+        assert quat_angle(res[name][:, :4].cpu().numpy().astype(np.float64), truth).max() < 0.02
+    st = res["weighted-filtered"].cpu().numpy().astype(np.float64)
+    for b in range(B):
+        n = int(sel["n_points"][b])
+        keep = sel["inliers"]["mask"][b, :n].cpu().numpy()
+        assert keep.sum() >= 0.5 * n
+        L = torch.diag_embed(sel["inv_cov"][b:b + 1, :n].sqrt()).cpu().numpy()[:, keep]
+        o = oracle.lm_solve(d["K"][b:b + 1].cpu().numpy(), sel["pts3d"][b:b + 1, :n].cpu().numpy()[:, keep],
+                            sel["pts2d"][b:b + 1, :n].cpu().numpy()[:, keep], L, sel["start"][b:b + 1].cpu().numpy())
         assert quat_angle(st[b:b + 1, :4], o["states"][:, :4].astype(np.float64)).max() <= 1e-6
         assert np.abs(st[b, 4:] - o["states"][0, 4:]).max() <= 1e-6 * np.abs(o["states"][0, 4:]).max()
