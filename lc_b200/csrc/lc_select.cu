@@ -13,7 +13,7 @@
 
 namespace lc {
 
-constexpr int kSelNT = 256;
+constexpr int kSelNT = 1024;
 
 __device__ __forceinline__ float sel_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 

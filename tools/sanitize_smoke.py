@@ -19,5 +19,35 @@ for (B, N) in [(3, 8), (2, 70), (2, 700), (2, 1300)]:
     w = (c.inv_std ** 2).requires_grad_(True)
     j, cv = weighted_pnp_jac_wrt_pts2d(c.pts2d, c.pose, c.K, c.pts3d, w, with_cov=True)
     (j.sum() + cv.sum()).backward()
+
+# rows f1-f4: dense / zebrapose producers, test-time decode, selection, initialiser, test-time chain, metrics, candidates
+from lc_b200.synth import make_dense_outputs, make_zebra_outputs, quat_to_matrix
+from lc_b200.dense import dense_loss_fwd_bwd
+from lc_b200.floatbits import nn_out_to_xyz
+from lc_b200.select import dense_point_select, solve_pnp_dense
+from lc_b200.evaluate import compute_pose_errors
+from lc_b200.symmetry import select_pose_2d, select_pose_3d
+
+for (H, W, sample) in [(16, 20, 1), (40, 36, 3)]:
+    d = {k: v.cuda() for k, v in make_dense_outputs(2, H, W, 3).items()}
+    dense_loss_fwd_bwd(d["xyz_noc"], d["logits"], d["scale"], d["noc_scale"], d["K"], d["pose"], d["bbox_3d"], sample=sample, top_left=(0, 0))
+    z = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in make_zebra_outputs(2, H, W, 4, (5, 4, 3)).items()}
+    dense_loss_fwd_bwd(None, z["logits"], z["scale"], z["noc_scale"], z["K"], z["pose"], z["bbox_3d"], sample=sample, top_left=(0, 0),
+                       noc_bin_logits=z["bin_logits"], noc_bin_raw=z["raw_bits"], msk_noc=z["msk_noc"], bit_cnt=(5, 4, 3),
+                       model_transform=z["model_transform"])
+    xyz = nn_out_to_xyz(z["bin_logits"], z["noc_scale"], model_transform=z["model_transform"], bit_cnt=(5, 4, 3))
+    nn_out_to_xyz(z["bin_logits"][:, :, :H - 1, :W - 1], z["noc_scale"], bit_cnt=(5, 4, 3))          # scalar path
+    ml = torch.randn(2, 1, H, W, device="cuda")
+    for mode in ("mask", "quantile", "quantile_in_mask"):
+        dense_point_select(xyz, ml, xyz_weight_logits=d["logits"], xyz_weights_scale=d["scale"], sample=sample, dense_point_select=mode, want_index=True)
+    solve_pnp_dense(d["K"], d["xyz_noc"].permute(0, 2, 3, 1), ml + 3, d["logits"], d["scale"], None, noc_scale=d["noc_scale"], sample=sample,
+                    solvers=("weighted", "weighted_filtered"))
+c = make_correspondences(3, 300, 2)
+Rg, Re = quat_to_matrix(c.pose[:, :4]).cuda(), quat_to_matrix(c.start[:, :4]).cuda()
+compute_pose_errors(Re, c.start[:, 4:].cuda(), Rg, c.pose[:, 4:].cuda(), torch.randn(2500, 3, dtype=torch.float64, device="cuda") * 50)
+c32 = c.to(torch.float32).to(device="cuda")
+candi = torch.cat((Rg.float(), c32.pose[:, 4:, None]), -1)[:, None].repeat(1, 5, 1, 1)
+select_pose_2d(c32.K, c32.pts3d, c32.pts2d, candi)
+select_pose_3d(c32.K, c32.pts3d, (c32.pts3d @ Rg.float().mT + c32.pose[:, None, 4:]) @ c32.K.mT, candi)
 torch.cuda.synchronize()
 print("sanitize smoke done")
