@@ -388,7 +388,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(a.pipeline), "kernel": kernel, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "launch_us": launch_s * 1e6,
-                "note": "arithmetic/latency bound, not HBM bound (DESIGN.md 4.3): ~1.5k instructions per point incl. an fp64 LM; frac is against the measured HBM copy peak as BASELINE.json asks"}
+                "note": "arithmetic/latency bound, not HBM bound (DESIGN.md 4.9): ~1.5k instructions per point incl. an fp64 LM; frac is against the measured HBM copy peak as BASELINE.json asks"}
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
