@@ -222,7 +222,6 @@ static int launch_res_m(const lc_args& a, cudaStream_t st) {
     const int nt = resident_threads_for(a.N, MODE);
     if (nt == 128) return launch_res_t<128, MODE>(a, st);
     if (nt == 192) return launch_res_t<192, MODE>(a, st);
-    if (nt == 320) return launch_res_t<320, MODE>(a, st);
     return launch_res_t<256, MODE>(a, st);
 }
 

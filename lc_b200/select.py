@@ -61,6 +61,9 @@ def dense_point_select(xyz: Tensor, msk_vis_logits: Tensor, *, xyz_weight_logits
     return out
 
 
+_select_points = dense_point_select   # solve_pnp_dense keeps the reference's cfg name `dense_point_select` as a keyword
+
+
 def solve_pnp_dense(K: Tensor, xyz: Tensor, msk_vis_logits: Tensor, xyz_weight_logits: Tensor, xyz_weights_scale: Tensor,
                     start: Optional[Tensor] = None, *, noc_scale: Optional[Tensor] = None, sample: int = 2,
                     dense_point_select: str = "quantile_in_mask", quantile: float = 0.2, seg_thresh: float = 0.5,
@@ -75,9 +78,9 @@ def solve_pnp_dense(K: Tensor, xyz: Tensor, msk_vis_logits: Tensor, xyz_weight_l
     Returns ``(dict name -> states (B,7), selection dict)`` with the reference's result names (``'weighted'``,
     ``'weighted-filtered'``)."""
     from .pnp import cer_solver, init_solver
-    sel = dense_point_select_fn(xyz, msk_vis_logits, xyz_weight_logits=xyz_weight_logits, xyz_weights_scale=xyz_weights_scale,
-                                noc_scale=noc_scale, sample=sample, dense_point_select=dense_point_select, quantile=quantile,
-                                seg_thresh=seg_thresh)
+    sel = _select_points(xyz, msk_vis_logits, xyz_weight_logits=xyz_weight_logits, xyz_weights_scale=xyz_weights_scale,
+                         noc_scale=noc_scale, sample=sample, dense_point_select=dense_point_select, quantile=quantile,
+                         seg_thresh=seg_thresh)
     inliers = None
     if start is None:
         invalid0, start, inliers = init_solver.solve(K, sel["pts3d"], sel["pts2d"], weights=sel["inv_cov"], n_points=sel["n_points"],
@@ -95,5 +98,3 @@ def solve_pnp_dense(K: Tensor, xyz: Tensor, msk_vis_logits: Tensor, xyz_weight_l
                                                     num_workers=4, filter_input_nan=True)[1]              # test.py:133
     return res, sel
 
-
-dense_point_select_fn = dense_point_select
