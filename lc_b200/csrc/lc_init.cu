@@ -15,7 +15,7 @@
 
 namespace lc {
 
-constexpr int kInitNT = 128;
+constexpr int kInitNT = 256;
 
 // smallest-eigenvalue eigenvector of a symmetric 4x4 (cyclic Jacobi, one thread)
 __device__ void sym4_min_eigvec(double A[4][4], double* v) {

@@ -113,3 +113,35 @@ def test_lc_op_inside_a_training_step():
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_operators_are_cuda_graph_capturable():
+    """The C ABI never allocates or synchronises, so a launch-bound inner loop (small batches) can be captured in a CUDA graph:
+    capture loss_fwd_bwd + the test-time chain once, replay on new inputs written into the static buffers."""
+    from lc_b200.cov_mixed import loss_fwd_bwd
+    from lc_b200.select import solve_pnp_dense
+    from lc_b200.synth import make_correspondences, make_dense_outputs
+    c = make_correspondences(4, 256, 0).to(torch.float32).to(device="cuda")
+    c2 = make_correspondences(4, 256, 1).to(torch.float32).to(device="cuda")
+    d = {k: v.cuda() for k, v in make_dense_outputs(4, 32, 32, 3).items()}
+    ml = torch.full((4, 1, 32, 32), 3.0, device="cuda")
+    static = dict(K=c.K.clone(), pose=c.pose.clone(), X=c.pts3d.clone(), x=c.pts2d.clone(), s=c.inv_std.clone(), bb=c.bbox_3d.clone())
+    run = lambda: (loss_fwd_bwd(static["K"], static["pose"], static["X"], static["x"], static["s"], None, static["bb"]),
+                   solve_pnp_dense(d["K"], d["xyz_noc"].permute(0, 2, 3, 1), ml, d["logits"], d["scale"], None, noc_scale=d["noc_scale"], sample=1))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run()                                           # warm-up outside the capture (library load, smem opt-in attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out, (res, sel) = run()
+    for src in (c, c2):
+        for k, v in zip(("K", "pose", "X", "x", "s", "bb"), (src.K, src.pose, src.pts3d, src.pts2d, src.inv_std, src.bbox_3d)):
+            static[k].copy_(v)
+        g.replay()
+        torch.cuda.synchronize()
+        eager = loss_fwd_bwd(src.K, src.pose, src.pts3d, src.pts2d, src.inv_std, None, src.bbox_3d)
+        assert torch.equal(out["loss"], eager["loss"]) and torch.equal(out["g_pts3d"], eager["g_pts3d"])
+    eager_res, _ = solve_pnp_dense(d["K"], d["xyz_noc"].permute(0, 2, 3, 1), ml, d["logits"], d["scale"], None, noc_scale=d["noc_scale"], sample=1)
+    assert torch.equal(res["weighted"], eager_res["weighted"])
