@@ -7,7 +7,7 @@
 //   * weighted DLT in normalised coordinates (K^-1 x, Hartley-normalised X), reduced analytically to a 4x4 symmetric
 //     eigenproblem: with S = sum w X~X~^T, Sx = sum w x X~X~^T, Sy, Sq = sum w (x^2+y^2) X~X~^T the rows of P = [p1;p2;p3]
 //     minimise sum w [(p1.X~ - x p3.X~)^2 + (p2.X~ - y p3.X~)^2]  =>  p1 = S^-1 Sx p3, p2 = S^-1 Sy p3,
-//     p3 = smallest eigenvector of Sq - Sx S^-1 Sx - Sy S^-1 Sy.  40 fp64 sums per pass;
+//     p3 = smallest eigenvector of Sq - Sx S^-1 Sx - Sy S^-1 Sy (inverse iteration).  40 fp64 sums per pass;
 //   * R from the first two rows of P (robust in the weak-perspective regime of small objects), r3 = r1 x r2;
 //   * IRLS: Cauchy weights on the pixel reprojection error with scale `reproj_thresh`, `irls_rounds` re-solves;
 //   * inlier mask = reprojection error < reproj_thresh under the returned pose (the role of RANSAC's inlier set).
@@ -17,52 +17,61 @@ namespace lc {
 
 constexpr int kInitNT = 256;
 
-// smallest-eigenvalue eigenvector of a symmetric 4x4 (cyclic Jacobi, one thread)
-__device__ void sym4_min_eigvec(double A[4][4], double* v) {
-    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
-    for (int sweep = 0; sweep < 12; ++sweep) {
-        double off = 0.0;
-        for (int p = 0; p < 4; ++p)
-            for (int q = p + 1; q < 4; ++q) off += A[p][q] * A[p][q];
-        double diag = 0.0;
-        for (int p = 0; p < 4; ++p) diag += A[p][p] * A[p][p];
-        if (off <= 1e-30 * diag) break;
-        for (int p = 0; p < 4; ++p)
-            for (int q = p + 1; q < 4; ++q) {
-                if (A[p][q] == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = rsqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 4; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq; }
-                for (int k = 0; k < 4; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk; }
-                for (int k = 0; k < 4; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq; }
-            }
-    }
-    int m = 0;
-    for (int k = 1; k < 4; ++k) if (A[k][k] < A[m][m]) m = k;
-    for (int k = 0; k < 4; ++k) v[k] = V[k][m];
-}
-
-// Cholesky solve of the SPD 4x4 S (full) for 4 right-hand sides at once: Z = S^-1 Bm.  false if S is not SPD.
-__device__ bool chol4_solve(const double S[4][4], const double Bm[4][4], double Z[4][4]) {
-    double L[4][4] = {};
+// Lower Cholesky factor of the SPD 4x4 S with reciprocal diagonal (no IEEE division / sqrt: rsqrt + multiplies).
+__device__ bool chol4(const double S[4][4], double L[4][4], double il[4]) {
     for (int j = 0; j < 4; ++j) {
         double d = S[j][j];
         for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-        if (!(d > 0.0)) return false;
-        L[j][j] = sqrt(d);
+        if (!(d > 0.0) || isinf(d)) return false;
+        il[j] = rsqrt(d);
+        L[j][j] = d * il[j];
         for (int i = j + 1; i < 4; ++i) {
             double v = S[i][j];
             for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-            L[i][j] = v / L[j][j];
+            L[i][j] = v * il[j];
         }
     }
+    return true;
+}
+__device__ void chol4_backsolve(const double L[4][4], const double il[4], const double* rhs, double* z) {
+    double y[4];
+    for (int i = 0; i < 4; ++i) { double v = rhs[i]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v * il[i]; }
+    for (int i = 3; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 4; ++k) v -= L[k][i] * z[k]; z[i] = v * il[i]; }
+}
+
+// Z = S^-1 Bm for 4 right-hand sides.  false if S is not SPD.
+__device__ bool chol4_solve(const double S[4][4], const double Bm[4][4], double Z[4][4]) {
+    double L[4][4] = {}, il[4];
+    if (!chol4(S, L, il)) return false;
     for (int c = 0; c < 4; ++c) {
-        double y[4];
-        for (int i = 0; i < 4; ++i) { double v = Bm[i][c]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v / L[i][i]; }
-        for (int i = 3; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 4; ++k) v -= L[k][i] * Z[k][c]; Z[i][c] = v / L[i][i]; }
+        double rhs[4], z[4];
+        for (int i = 0; i < 4; ++i) rhs[i] = Bm[i][c];
+        chol4_backsolve(L, il, rhs, z);
+        for (int i = 0; i < 4; ++i) Z[i][c] = z[i];
     }
     return true;
+}
+
+// Eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 4x4 by inverse iteration on D + mu I
+// (mu = 1e-12 trace keeps the factorisation defined for noise-free data, where the smallest eigenvalue is 0 up to rounding).
+// The eigenvalue gap of this problem is the ratio of the noise to the signal energy (1e-2 .. 1e-6), so kInvIters steps reach
+// fp64 precision; a fully serial cyclic Jacobi sweep costs ~10x more dependent fp64 operations.
+constexpr int kInvIters = 5;
+__device__ bool sym4_min_eigvec(const double D[4][4], double* v) {
+    const double tr = D[0][0] + D[1][1] + D[2][2] + D[3][3];
+    if (!(tr > 0.0) || isinf(tr)) return false;
+    double A[4][4], L[4][4] = {}, il[4];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) A[r][c] = D[r][c] + (r == c ? 1e-12 * tr : 0.0);
+    if (!chol4(A, L, il)) return false;
+    v[0] = 0.1; v[1] = 0.1; v[2] = 0.1; v[3] = 1.0;
+    for (int it = 0; it < kInvIters; ++it) {
+        double w[4];
+        chol4_backsolve(L, il, v, w);
+        const double nrm = rsqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
+        for (int k = 0; k < 4; ++k) v[k] = w[k] * nrm;
+    }
+    return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]) && isfinite(v[3]);
 }
 
 struct InitShared {
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(kInitNT) lc_init_kernel(const lc_init_args d) 
         }
         __syncthreads();
     }
-    const double c0 = s.cen[0], c1 = s.cen[1], c2 = s.cen[2], isc = 1.0 / s.scale;
+    const double c0 = s.cen[0], c1 = s.cen[1], c2 = s.cen[2], isc = 1.0 / s.scale, ithr2 = 1.0 / (thr * thr);
 
     for (int round = 0; round <= d.irls_rounds; ++round) {
         // ---- 40 weighted sums ----
@@ -126,13 +135,13 @@ __global__ void __launch_bounds__(kInitNT) lc_init_kernel(const lc_init_args d) 
             if (robust) {
                 const double p0 = R[0] * X0 + R[1] * X1 + R[2] * X2 + t[0], p1 = R[3] * X0 + R[4] * X1 + R[5] * X2 + t[1],
                              p2 = R[6] * X0 + R[7] * X1 + R[8] * X2 + t[2];
-                const double h2 = s.K[6] * p0 + s.K[7] * p1 + s.K[8] * p2;
-                const double eu = (s.K[0] * p0 + s.K[1] * p1 + s.K[2] * p2) / h2 - u, ev = (s.K[3] * p0 + s.K[4] * p1 + s.K[5] * p2) / h2 - v;
-                const double e2 = (eu * eu + ev * ev) / (thr * thr);
-                wt *= (h2 > 0.0 && isfinite(e2)) ? 1.0 / (1.0 + e2) : 0.0;     // Cauchy
+                const double h2 = s.K[6] * p0 + s.K[7] * p1 + s.K[8] * p2, ih2 = fast_rcp(h2);
+                const double eu = (s.K[0] * p0 + s.K[1] * p1 + s.K[2] * p2) * ih2 - u, ev = (s.K[3] * p0 + s.K[4] * p1 + s.K[5] * p2) * ih2 - v;
+                const double e2 = (eu * eu + ev * ev) * ithr2;
+                wt *= (h2 > 0.0 && isfinite(e2)) ? fast_rcp(1.0 + e2) : 0.0;     // Cauchy
             }
-            const double zn = s.Ki[6] * u + s.Ki[7] * v + s.Ki[8];
-            const double xh = (s.Ki[0] * u + s.Ki[1] * v + s.Ki[2]) / zn, yh = (s.Ki[3] * u + s.Ki[4] * v + s.Ki[5]) / zn;
+            const double izn = fast_rcp(s.Ki[6] * u + s.Ki[7] * v + s.Ki[8]);
+            const double xh = (s.Ki[0] * u + s.Ki[1] * v + s.Ki[2]) * izn, yh = (s.Ki[3] * u + s.Ki[4] * v + s.Ki[5]) * izn;
             const double Y[4] = {(X0 - c0) * isc, (X1 - c1) * isc, (X2 - c2) * isc, 1.0};
             const double wq = wt * (xh * xh + yh * yh), wx = wt * xh, wy = wt * yh;
             int k = 0;
@@ -169,8 +178,8 @@ __global__ void __launch_bounds__(kInitNT) lc_init_kernel(const lc_init_args d) 
                     }
                 for (int r = 0; r < 4; ++r)
                     for (int c = r + 1; c < 4; ++c) D[r][c] = D[c][r] = 0.5 * (D[r][c] + D[c][r]);
-                double p3[4], p1[4], p2[4];
-                sym4_min_eigvec(D, p3);
+                double p3[4] = {0, 0, 0, 1}, p1[4], p2[4];
+                if (!sym4_min_eigvec(D, p3)) s.ok = 0;
                 for (int r = 0; r < 4; ++r) {
                     p1[r] = Zx[r][0] * p3[0] + Zx[r][1] * p3[1] + Zx[r][2] * p3[2] + Zx[r][3] * p3[3];
                     p2[r] = Zy[r][0] * p3[0] + Zy[r][1] * p3[1] + Zy[r][2] * p3[2] + Zy[r][3] * p3[3];

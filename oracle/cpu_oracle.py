@@ -449,8 +449,17 @@ def pnp_init(K, pts3d, pts2d, weights=None, reproj_thresh=3.0, irls_rounds=3):
         Zx, Zy = np.linalg.solve(S, Sx), np.linalg.solve(S, Sy)
         D = Sq - Sx @ Zx - Sy @ Zy
         D = 0.5 * (D + D.T)
-        ev, V = np.linalg.eigh(D)
-        p3 = V[:, 0]
+        tr = np.trace(D)
+        if not (tr > 0):
+            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+        try:
+            Lc = np.linalg.cholesky(D + 1e-12 * tr * np.eye(4))      # inverse iteration, as lc_init.cu::sym4_min_eigvec
+        except np.linalg.LinAlgError:
+            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+        p3 = np.array([0.1, 0.1, 0.1, 1.0])
+        for _ in range(5):
+            p3 = np.linalg.solve(Lc.T, np.linalg.solve(Lc, p3))
+            p3 = p3 / np.linalg.norm(p3)
         P = np.stack((Zx @ p3, Zy @ p3, p3))
         Q = np.concatenate((P[:, :3] / sc, (P[:, 3] - P[:, :3] @ cen / sc)[:, None]), 1)
         if Q[2, :3] @ cen + Q[2, 3] < 0:

@@ -1,3 +1,5 @@
+"""Component timings of the test-time chain at the zycbv test shape (128x128, dense_sample 1): selection, initialiser, LM on the
+padded batch vs LM on a batch trimmed to max(n_points).  Run on the GPU box: python tools/bench_chain_components.py"""
 import sys, torch, time
 sys.path.insert(0, '/root/repo')
 from lc_b200.synth import make_dense_outputs
