@@ -183,6 +183,23 @@ typedef struct lc_decode_args {
 int lc_b200_noc_bin_decode(const lc_decode_args* a, void* cuda_stream);
 
 /*
+ * ZebraPose target coding (row f3): floatbits.nn_noc2target (floatbits.py:13-31, 76-97), the producer of the ground-truth bits
+ * the training decode consumes (losses.py:64, 130-136): per axis ints = round(clamp((noc+1)*max/2, 0, max)), MSB-first binary
+ * `raw`, Gray code `mod` (mod_j = raw_j xor raw_{j-1}) with the two leading bits inverted under a black background.
+ * Outputs are written channel-last, (B,H,W,C) bytes, the storage the reference's permuted views have.
+ */
+typedef struct lc_encode_args {
+    int32_t abi_version, B, H, W;
+    int32_t bit_cnt[3];
+    int32_t black_background;
+    lc_view noc;       /* (B,H,W,3) fp32, any strides [batch,row,col,component] */
+    uint8_t* mod_bits; /* out (B,H,W,C) 0/1 bytes, or NULL */
+    uint8_t* raw_bits; /* out (B,H,W,C) 0/1 bytes, or NULL */
+} lc_encode_args;
+
+int lc_b200_noc_bin_encode(const lc_encode_args* a, void* cuda_stream);
+
+/*
  * Test-time point selection ("next" row f2): the selection half of test.solve_pnp_dense (test.py:67-119) on the device.
  *   weights  = softmax(weight logits over 2*H*W, or per channel when weights_scale is (B,2)) * weights_scale   test.py:84-88
  *   sub-sample every `sample`-th pixel from (0,0): pts2d grid, inv_std, xyz, seg mask                           losses.py:142-161

@@ -32,7 +32,7 @@ ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",
            "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd",
            "lc_b200_dense_loss_fwd_bwd", "lc_b200_noc_bin_decode", "lc_b200_dense_select", "lc_b200_pose_errors",
-           "lc_b200_select_pose", "lc_b200_pnp_init")
+           "lc_b200_select_pose", "lc_b200_pnp_init", "lc_b200_noc_bin_encode")
 
 
 class NativeLibraryError(RuntimeError):
@@ -95,6 +95,12 @@ class lc_select_args(C.Structure):
                  ("seg_thresh", C.c_float), ("reserved1", C.c_float)]
                 + [(f, lc_view) for f in ("xyz", "noc_scale", "weights", "logits", "weights_scale", "msk_logits", "pts3d", "pts2d", "inv_cov")]
                 + [("index", C.c_void_p), ("n_points", C.c_void_p)])
+
+
+class lc_encode_args(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("bit_cnt", C.c_int32 * 3), ("black_background", C.c_int32), ("noc", lc_view),
+                ("mod_bits", C.c_void_p), ("raw_bits", C.c_void_p)]
 
 
 class lc_init_args(C.Structure):
@@ -167,7 +173,8 @@ def lib() -> C.CDLL:
         for name in EXPORTS[3:]:
             argt = {"lc_b200_dense_loss_fwd_bwd": lc_dense_args, "lc_b200_noc_bin_decode": lc_decode_args,
                     "lc_b200_dense_select": lc_select_args, "lc_b200_pose_errors": lc_eval_args,
-                    "lc_b200_select_pose": lc_candi_args, "lc_b200_pnp_init": lc_init_args}.get(name, lc_args)
+                    "lc_b200_select_pose": lc_candi_args, "lc_b200_pnp_init": lc_init_args,
+                    "lc_b200_noc_bin_encode": lc_encode_args}.get(name, lc_args)
             getattr(handle, name).argtypes = [C.POINTER(argt), C.c_void_p]
             getattr(handle, name).restype = C.c_int
         if handle.lc_b200_abi_version() != ABI_VERSION:

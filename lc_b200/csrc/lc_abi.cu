@@ -104,6 +104,18 @@ static int dispatch_decode(const lc_decode_args* d, void* stream) {
     return check_launch(launch_decode(*d, static_cast<cudaStream_t>(stream)));
 }
 
+static int dispatch_encode(const lc_encode_args* d, void* stream) {
+    g_launches = 0;
+    if (!d) return fail(LC_E_NULL, "args is NULL");
+    if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
+    if (d->B < 0 || d->H <= 0 || d->W <= 0) return fail(LC_E_BADARG, "bad B / H / W");
+    for (int k = 0; k < 3; ++k)
+        if (d->bit_cnt[k] < 1 || d->bit_cnt[k] > 16) return fail(LC_E_BADARG, "bit_cnt entries must be in 1..16");
+    if (d->B == 0) return LC_OK;
+    if (!d->noc.ptr || (!d->mod_bits && !d->raw_bits)) return fail(LC_E_NULL, "noc and at least one output are required");
+    return check_launch(launch_encode(*d, static_cast<cudaStream_t>(stream)));
+}
+
 static int dispatch_select(const lc_select_args* d, void* stream) {
     g_launches = 0;
     if (!d) return fail(LC_E_NULL, "args is NULL");
@@ -171,6 +183,7 @@ int lc_b200_pnp_jac_cov(const lc_args* a, void* stream) { return lc::dispatch_ja
 int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* stream) { return lc::dispatch_jac(a, true, stream); }
 int lc_b200_dense_loss_fwd_bwd(const lc_dense_args* a, void* stream) { return lc::dispatch_dense(a, stream); }
 int lc_b200_noc_bin_decode(const lc_decode_args* a, void* stream) { return lc::dispatch_decode(a, stream); }
+int lc_b200_noc_bin_encode(const lc_encode_args* a, void* stream) { return lc::dispatch_encode(a, stream); }
 int lc_b200_dense_select(const lc_select_args* a, void* stream) { return lc::dispatch_select(a, stream); }
 int lc_b200_pnp_init(const lc_init_args* a, void* stream) { return lc::dispatch_init(a, stream); }
 int lc_b200_pose_errors(const lc_eval_args* a, void* stream) { return lc::dispatch_eval(a, stream); }

@@ -368,6 +368,45 @@ __global__ void __launch_bounds__(256) lc_decode_kernel_v4(const lc_decode_args 
     __stcs(out + 2, make_float4(o[8], o[9], o[10], o[11]));
 }
 
+// Target coding (floatbits.py:76-97): one thread per pixel, C bytes per output array, channel-last.
+__global__ void __launch_bounds__(256) lc_encode_kernel(const lc_encode_args d) {
+    const int HW = d.H * d.W;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= static_cast<int64_t>(d.B) * HW) return;
+    const int b = static_cast<int>(gid / HW), p = static_cast<int>(gid - static_cast<int64_t>(b) * HW);
+    const int y = p / d.W, x = p - y * d.W;
+    const int C_ = d.bit_cnt[0] + d.bit_cnt[1] + d.bit_cnt[2];
+    const int64_t o = b * d.noc.stride[0] + y * d.noc.stride[1] + x * d.noc.stride[2];
+    unsigned char* mo = d.mod_bits ? d.mod_bits + gid * C_ : nullptr;
+    unsigned char* ro = d.raw_bits ? d.raw_bits + gid * C_ : nullptr;
+    int c0 = 0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int N = d.bit_cnt[ax];
+        const float mx = static_cast<float>((1 << N) - 1);
+        // ints = torch.clamp_((numbers + 1) * (max_num * 0.5), 0, max_num).round_().to(int32)   (floatbits.py:87-88)
+        const float v = __fmul_rn(__fadd_rn(ldf(d.noc, o + ax * d.noc.stride[3]), 1.f), mx * 0.5f);
+        const int iv = static_cast<int>(rintf(fminf(fmaxf(v, 0.f), mx)));     // NaN -> 0 like clamp's NaN propagation + int cast on CPU
+        int prev = 0;
+        for (int j = 0; j < N; ++j) {
+            const int bit = (iv >> (N - 1 - j)) & 1;
+            int mod = bit ^ prev;                                              // floatbits.py:91-92
+            if (d.black_background && j < 2) mod ^= 1;                         // :93-94
+            if (ro) ro[c0 + j] = static_cast<unsigned char>(bit);
+            if (mo) mo[c0 + j] = static_cast<unsigned char>(mod);
+            prev = bit;
+        }
+        c0 += N;
+    }
+}
+
+int launch_encode(const lc_encode_args& d, cudaStream_t st) {
+    const int64_t total = static_cast<int64_t>(d.B) * d.H * d.W;
+    if (total == 0) return 0;
+    lc_encode_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d);
+    return static_cast<int>(cudaGetLastError());
+}
+
 int launch_decode(const lc_decode_args& d, cudaStream_t st) {
     const int64_t HW = static_cast<int64_t>(d.H) * d.W, total = static_cast<int64_t>(d.B) * HW;
     if (total == 0) return 0;

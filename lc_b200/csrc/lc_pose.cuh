@@ -791,6 +791,7 @@ bool resident_supported(const lc_args& a, int mode);
 int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st);
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
 int launch_decode(const lc_decode_args& d, cudaStream_t st);
+int launch_encode(const lc_encode_args& d, cudaStream_t st);
 int launch_select(const lc_select_args& d, cudaStream_t st);
 int launch_init(const lc_init_args& d, cudaStream_t st);
 int launch_pose_errors(const lc_eval_args& d, cudaStream_t st);

@@ -61,3 +61,25 @@ def nn_logits2noc(logits: Tensor, bit_cnt: Union[int, Sequence[int]]) -> Tensor:
     """``floatbits.nn_logits2noc`` without LUT (``floatbits.py:33-47``): ``(B,C,H,W)`` -> ``noc (B,H,W,3)``."""
     ones = torch.ones(1, 3, dtype=torch.float32, device=logits.device)
     return nn_out_to_xyz(logits, ones, bit_cnt=bit_cnt)
+
+
+def nn_noc2target(noc: Tensor, bit_cnt: Union[int, Sequence[int]]):
+    """``floatbits.nn_noc2target`` (``floatbits.py:13-31``): ``noc (B,H,W,3)`` in (-1,1) -> ``(mod_bits, bits)``, both bool
+    ``(B,C,H,W)`` views of channel-last storage exactly like the reference returns (``:24-25, 31``): the Gray-coded training
+    targets and the raw binary bits ``lc_b200.dense.dense_pose_loss_noc_bin`` consumes."""
+    dev = nat.check_cuda(noc)
+    if noc.dtype != torch.float32:
+        raise TypeError("nn_noc2target takes float32 coordinates")
+    B, H, W, _ = noc.shape
+    bits = [int(bit_cnt)] * 3 if isinstance(bit_cnt, int) else [int(v) for v in bit_cnt]
+    C_ = sum(bits)
+    mod = torch.empty(B, H, W, C_, dtype=torch.uint8, device=dev)
+    raw = torch.empty(B, H, W, C_, dtype=torch.uint8, device=dev)
+    a = nat.lc_encode_args()
+    a.abi_version, a.B, a.H, a.W = nat.ABI_VERSION, B, H, W
+    a.bit_cnt[:] = bits
+    a.black_background = int(_black_background)
+    a.noc = nat.view_of(noc)
+    a.mod_bits, a.raw_bits = mod.data_ptr(), raw.data_ptr()
+    nat.call("lc_b200_noc_bin_encode", a, dev)
+    return mod.view(torch.bool).permute(0, 3, 1, 2), raw.view(torch.bool).permute(0, 3, 1, 2)

@@ -177,12 +177,15 @@ def noc_to_bits(noc, bit_cnt, black_background=True):
     """floatbits.py:76-97 mod_noc2bits_bb / :13-31 nn_noc2target: noc (B,H,W,3) in (-1,1) -> (mod_bits, raw_bits), both
     (B,sum(bit_cnt),H,W) bool.  raw = MSB-first binary of round(clamp((noc+1)*max/2, 0, max)); mod = Gray code of it with
     the two leading bits inverted under a black background."""
-    noc = np.asarray(noc, np.float64)
+    noc = np.asarray(noc)
+    if noc.dtype not in (np.float32, np.float64):
+        noc = noc.astype(np.float64)
+    ft = noc.dtype.type                      # the reference computes in the tensor's dtype (fp32 in training)
     bit_cnt, _ = _axis_slices(bit_cnt)
     mods, raws = [], []
     for a, N in enumerate(bit_cnt):
         mx = 2 ** N - 1
-        ints = np.rint(np.clip((noc[..., a] + 1) * (mx * 0.5), 0, mx)).astype(np.int64)   # torch.round = half-to-even = rint
+        ints = np.rint(np.clip((noc[..., a] + ft(1)) * ft(mx * 0.5), ft(0), ft(mx))).astype(np.int64)   # torch.round = half-to-even = rint
         raw = ((ints[..., None] >> np.arange(N - 1, -1, -1)) & 1).astype(bool)
         mod = raw.copy()
         mod[..., 1:] ^= raw[..., :-1]
