@@ -40,6 +40,19 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
         return fail(LC_E_BADARG, "solve_loss takes inverse std weights (weight_mode = LC_W_INV_STD)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && resident_supported(*a, mode)) return check_launch(launch_resident_pose(*a, mode, st));
+    if (!(a->flags & LC_FLAG_FORCE_STREAMING)) {
+        // Ragged batch padded beyond the resident limit (the test-time chain pads to the full map, test.py:106-119): poses with
+        // n_points <= cap take the resident kernel, the others the streaming kernel; both launches cover the whole grid and
+        // each CTA decides from n_points[b] alone, so no host synchronisation is needed.
+        const int cap = resident_split_capacity(*a, mode);
+        if (cap > 0) {
+            int rc = check_launch(launch_resident_pose(*a, mode, st, cap));
+            if (rc != LC_OK) return rc;
+            rc = check_launch(launch_stream_pose(*a, mode, st, cap));
+            if (rc == LC_OK) g_launches = 2;
+            return rc;
+        }
+    }
     if (mode == (MODE_LM | MODE_LC) && a->N <= 64 && a->state.ptr) {
         // Tiny N (sparse keypoints): the per-pose 6x6 / trust-region sections dominate and the fused variant carries the
         // register footprint of both phases; two back-to-back launches (solve, then loss at the solved pose read back

@@ -785,10 +785,11 @@ __device__ __forceinline__ void lc_six_warp(const lc_args& a, PoseShared& s, int
 }
 
 // host-side launch entry points implemented in lc_stream.cu / lc_resident.cu (return cudaError_t as int)
-int launch_stream_pose(const lc_args& a, int mode, cudaStream_t st);
+int launch_stream_pose(const lc_args& a, int mode, cudaStream_t st, int n_skip_le = -1);
 int launch_stream_jac(const lc_args& a, bool bwd, cudaStream_t st);
 bool resident_supported(const lc_args& a, int mode);
-int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st);
+int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st, int cap = 0);
+int resident_split_capacity(const lc_args& a, int mode);
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
 int launch_decode(const lc_decode_args& d, cudaStream_t st);
 int launch_encode(const lc_encode_args& d, cudaStream_t st);

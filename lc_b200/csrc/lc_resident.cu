@@ -24,13 +24,14 @@
 namespace lc {
 
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask) {
+__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask, int n_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
     const ResLayout l = res_layout(smem_raw, npad);
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
+    if (n > n_max) return;   // ragged batch split by n_points: this pose belongs to the streaming launch (lc_abi.cu)
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
 #ifdef LC_TIMING
     if (tid == 0) for (int k = 0; k < 8; ++k) s.fin_timing[k] = 0;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             if (tid == 0) mbar_init(&s.tma_bar, 1);
             __syncthreads();
             if (tid == 0) {
-                const unsigned slab = static_cast<unsigned>(a.N) * 4u;
+                const unsigned slab = static_cast<unsigned>(min(a.N, npad)) * 4u;   // npad < N only for split ragged batches
                 mbar_expect_tx(&s.tma_bar, slab * ((tma3 ? 3u : 0u) + (tma2 ? 2u : 0u)));
                 if (tma3) { tma_load_1d(l.A0, p3, slab, &s.tma_bar); tma_load_1d(l.A1, p3 + s3c, slab, &s.tma_bar); tma_load_1d(l.A2, p3 + 2 * s3c, slab, &s.tma_bar); }
                 if (tma2) { tma_load_1d(l.B0, p2, slab, &s.tma_bar); tma_load_1d(l.B1, p2 + s2c, slab, &s.tma_bar); }
@@ -201,8 +202,9 @@ static int tma_mask_for(const lc_args& a) {
 }
 
 template <int NT, int MODE>
-static int launch_res_t(const lc_args& a, cudaStream_t st) {
-    const size_t smem = resident_smem_bytes(a.N);
+static int launch_res_t(const lc_args& a, cudaStream_t st, int cap) {
+    const int n_res = cap > 0 ? cap : a.N;   // points held in shared memory per pose
+    const size_t smem = resident_smem_bytes(n_res);
     static bool configured[64] = {};   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -211,26 +213,39 @@ static int launch_res_t(const lc_args& a, cudaStream_t st) {
         if (e != cudaSuccess) return static_cast<int>(e);
         configured[dev] = true;
     }
-    lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(a.N), tma_mask_for(a));
+    lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(n_res), tma_mask_for(a), cap > 0 ? cap : 0x7fffffff);
     return static_cast<int>(cudaGetLastError());
 }
 
 template <int MODE>
-static int launch_res_m(const lc_args& a, cudaStream_t st) {
+static int launch_res_m(const lc_args& a, cudaStream_t st, int cap) {
     // 256 threads x 2 CTAs per SM (20 B/point of shared memory): one CTA's 6x6 / trust-region sections and loads
     // overlap the other CTA's point passes
-    const int nt = resident_threads_for(a.N, MODE);
-    if (nt == 128) return launch_res_t<128, MODE>(a, st);
-    if (nt == 192) return launch_res_t<192, MODE>(a, st);
-    return launch_res_t<256, MODE>(a, st);
+    const int nt = resident_threads_for(cap > 0 ? cap : a.N, MODE);
+    if (nt == 128) return launch_res_t<128, MODE>(a, st, cap);
+    if (nt == 192) return launch_res_t<192, MODE>(a, st, cap);
+    return launch_res_t<256, MODE>(a, st, cap);
 }
 
-int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st) {
+// cap > 0: ragged batch whose padded N exceeds the resident limit; only poses with n_points <= cap are processed here
+int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st, int cap) {
     switch (mode) {
-        case MODE_LM: return launch_res_m<MODE_LM>(a, st);
-        case MODE_LC: return launch_res_m<MODE_LC>(a, st);
-        default: return launch_res_m<MODE_LM | MODE_LC>(a, st);
+        case MODE_LM: return launch_res_m<MODE_LM>(a, st, cap);
+        case MODE_LC: return launch_res_m<MODE_LC>(a, st, cap);
+        default: return launch_res_m<MODE_LM | MODE_LC>(a, st, cap);
     }
+}
+
+// Ragged batches (n_points given) whose padded N does not fit: the poses with n_points <= cap still can take the resident
+// kernel.  cap = the largest point count that leaves two CTAs per SM; 0 when the split does not apply.
+int resident_split_capacity(const lc_args& a, int mode) {
+    if (!a.n_points || a.dtype != LC_F32 || a.N < kResidentMinN) return 0;
+    if ((mode & MODE_LM) && a.weight_mode != LC_W_ICOV_DIAG && a.weight_mode != LC_W_INV_STD) return 0;
+    const size_t per_cta = static_cast<size_t>(max_optin_smem()) / 2;
+    const size_t fixed = resident_smem_bytes(0) + 1024;
+    if (per_cta <= fixed) return 0;
+    const int cap = static_cast<int>((per_cta - fixed) / 20) & ~3;
+    return cap >= kResidentMinN && cap < a.N ? cap : 0;
 }
 
 }  // namespace lc

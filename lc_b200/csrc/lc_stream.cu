@@ -178,11 +178,12 @@ __device__ __forceinline__ void lm_eval_pass(const lc_args& a, PoseShared& s, in
 // the fused per-pose kernel (streaming)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NT, int MODE>
-__global__ void __launch_bounds__(NT, (NT <= 64) ? (1024 / NT / 2) : 1) lc_pose_kernel(const lc_args a) {
+__global__ void __launch_bounds__(NT, (NT <= 64) ? (1024 / NT / 2) : 1) lc_pose_kernel(const lc_args a, int n_skip_le) {
     __shared__ PoseShared s;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
+    if (n <= n_skip_le) return;   // ragged batch split by n_points: this pose was handled by the resident launch (lc_abi.cu)
     const bool sanitize = (a.flags & LC_FLAG_NAN_TO_NUM) != 0;
 
     // ---- pose constants ----
@@ -602,22 +603,23 @@ static int stream_threads_for(int n) {
 }
 
 template <typename T, int MODE>
-static int launch_pose_t(const lc_args& a, cudaStream_t st) {
+static int launch_pose_t(const lc_args& a, cudaStream_t st, int skip) {
     switch (stream_threads_for(a.N)) {
-        case 32: lc_pose_kernel<T, 32, MODE><<<a.B, 32, 0, st>>>(a); break;
-        case 64: lc_pose_kernel<T, 64, MODE><<<a.B, 64, 0, st>>>(a); break;
-        case 128: lc_pose_kernel<T, 128, MODE><<<a.B, 128, 0, st>>>(a); break;
-        default: lc_pose_kernel<T, 256, MODE><<<a.B, 256, 0, st>>>(a); break;
+        case 32: lc_pose_kernel<T, 32, MODE><<<a.B, 32, 0, st>>>(a, skip); break;
+        case 64: lc_pose_kernel<T, 64, MODE><<<a.B, 64, 0, st>>>(a, skip); break;
+        case 128: lc_pose_kernel<T, 128, MODE><<<a.B, 128, 0, st>>>(a, skip); break;
+        default: lc_pose_kernel<T, 256, MODE><<<a.B, 256, 0, st>>>(a, skip); break;
     }
     return static_cast<int>(cudaGetLastError());
 }
 
-int launch_stream_pose(const lc_args& a, int mode, cudaStream_t st) {
+int launch_stream_pose(const lc_args& a, int mode, cudaStream_t st, int n_skip_le) {
     const bool f32 = a.dtype == LC_F32;
+    const int k = n_skip_le;
     switch (mode) {
-        case MODE_LM: return f32 ? launch_pose_t<float, MODE_LM>(a, st) : launch_pose_t<double, MODE_LM>(a, st);
-        case MODE_LC: return f32 ? launch_pose_t<float, MODE_LC>(a, st) : launch_pose_t<double, MODE_LC>(a, st);
-        default: return f32 ? launch_pose_t<float, MODE_LM | MODE_LC>(a, st) : launch_pose_t<double, MODE_LM | MODE_LC>(a, st);
+        case MODE_LM: return f32 ? launch_pose_t<float, MODE_LM>(a, st, k) : launch_pose_t<double, MODE_LM>(a, st, k);
+        case MODE_LC: return f32 ? launch_pose_t<float, MODE_LC>(a, st, k) : launch_pose_t<double, MODE_LC>(a, st, k);
+        default: return f32 ? launch_pose_t<float, MODE_LM | MODE_LC>(a, st, k) : launch_pose_t<double, MODE_LM | MODE_LC>(a, st, k);
     }
 }
 

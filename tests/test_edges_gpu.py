@@ -89,3 +89,34 @@ def test_fp64_tensors_through_the_python_operators(oracle):
     assert rel_err(p3.grad.cpu().numpy(), ref["g_pts3d"]) <= 1e-9
     inv, st = cer_solver.solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start)
     assert st.dtype == torch.float64 and not inv["invalids"].any()
+
+
+def test_ragged_batch_padded_beyond_the_resident_limit_is_split_by_n_points(oracle):
+    """The test-time chain pads to the full map (N = 16384 at 128x128) while n_points is a few thousand: poses that fit take
+    the shared-memory resident kernel, the rest the streaming kernel, two launches, no host sync.  Every pose must equal the
+    CPU oracle run on its own ragged point set, whichever kernel took it."""
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200.fused import solve_and_loss
+    from lc_b200 import _native as nat
+    N = 12000
+    npts = [100, 3000, 4900, 5100, 9000, 12000]
+    B = len(npts)
+    c = make_correspondences(B, N, 5).to(torch.float32)
+    n_t = torch.tensor(npts, dtype=torch.int32)
+    d = c.to(device="cuda")
+    o = lm_solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start, n_t.cuda(), weight_mode=nat.W_ICOV_DIAG)
+    s = lm_solve(d.K, d.pts3d, d.pts2d, d.inv_std ** 2, d.start, n_t.cuda(), weight_mode=nat.W_ICOV_DIAG, force_streaming=True)
+    assert nat.lib().lc_b200_last_launch_count() == 1
+    st, ss = o["states"].cpu().numpy().astype(np.float64), s["states"].cpu().numpy().astype(np.float64)
+    assert quat_angle(st[:, :4], ss[:, :4]).max() <= 1e-7 and np.array_equal(o["iters"].cpu().numpy(), s["iters"].cpu().numpy())
+    for b, n in enumerate(npts):
+        L = torch.diag_embed(c.inv_std[b:b + 1, :n]).numpy()
+        ref = oracle.lm_solve(c.K[b:b + 1].numpy(), c.pts3d[b:b + 1, :n].numpy(), c.pts2d[b:b + 1, :n].numpy(), L, c.start[b:b + 1].numpy())
+        assert quat_angle(st[b:b + 1, :4], ref["states"][:, :4].astype(np.float64)).max() <= 1e-6, n
+        assert int(o["iters"][b]) == int(ref["iters"][0]) and int(o["invalid"][b]) == int(ref["invalid"][0])
+    f = solve_and_loss(d.K, d.start, planar_view(d.pts3d), d.pts2d, planar_view(d.inv_std), None, d.bbox_3d, need=(True, False, True))
+    assert f["launches"] == 1                                   # no n_points: one streaming launch
+    args = dict(K=d.K, pose=d.start, pts3d=d.pts3d, pts2d=d.pts2d, weights=d.inv_std ** 2, n_points=n_t.cuda(),
+                state=torch.empty(B, 7, device="cuda"), invalid=torch.empty(B, dtype=torch.int32, device="cuda"),
+                weight_mode=nat.W_ICOV_DIAG, flags=nat.FLAG_TOL_NEEDS_SUCCESS)
+    assert nat.call("lc_b200_lm_solve", nat.make_args(B, N, torch.float32, **args), d.K.device) == 2   # resident + streaming

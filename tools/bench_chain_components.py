@@ -5,10 +5,10 @@ sys.path.insert(0, '/root/repo')
 from lc_b200.synth import make_dense_outputs
 from lc_b200.select import solve_pnp_dense, dense_point_select
 from lc_b200.pnp import cer_solver, init_solver
-for B in (32, 256):
+for B, rows_out in ((32, 40), (256, 40), (32, 88), (256, 88)):      # object mask = 69 % / 31 % of the crop
     d = make_dense_outputs(8, 128, 128, 80)
     cu = {k: torch.cat([v] * (B // 8)).cuda() for k, v in d.items()}
-    ml = torch.full((B, 1, 128, 128), 3.0, device="cuda"); ml[:, :, :40] = -3
+    ml = torch.full((B, 1, 128, 128), 3.0, device="cuda"); ml[:, :, :rows_out] = -3
     xyz = cu["xyz_noc"].permute(0, 2, 3, 1)
     def t(fn, n=20):
         for _ in range(3): fn()
