@@ -16,6 +16,7 @@
 namespace lc {
 
 constexpr int kInitNT = 256;
+constexpr int kInitMaxPts = 1024;   // correspondences used for the DLT / IRLS sums (sub-sampled by stride when there are more)
 
 // Lower Cholesky factor of the SPD 4x4 S with reciprocal diagonal (no IEEE division / sqrt: rsqrt + multiplies).
 __device__ bool chol4(const double S[4][4], double L[4][4], double il[4]) {
@@ -101,16 +102,20 @@ __global__ void __launch_bounds__(kInitNT) lc_init_kernel(const lc_init_args d) 
         s.Ki[6] = c02 * idet; s.Ki[7] = (R[1] * R[6] - R[0] * R[7]) * idet; s.Ki[8] = (R[0] * R[4] - R[1] * R[3]) * idet;
         s.ok = n >= 6 ? 1 : 0;
     }
+    // A start pose does not need every correspondence: the sums run over every `step`-th point (about kInitMaxPts of them);
+    // the inlier mask at the end covers all points.
+    const int step = n > kInitMaxPts ? (n + kInitMaxPts - 1) / kInitMaxPts : 1;
+    const int n_used = (n + step - 1) / step;
     // ---- Hartley normalisation of the model points ----
     {
         double acc[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = tid; i < n; i += kInitNT) {
+        for (int i = tid * step; i < n; i += kInitNT * step) {
             const double a = X[i * Xn], bb = X[i * Xn + Xc], c = X[i * Xn + 2 * Xc];
             acc[0] += a; acc[1] += bb; acc[2] += c; acc[3] += a * a; acc[4] += bb * bb; acc[5] += c * c;
         }
         block_reduce<6, kInitNT>(acc, s.red, s.fin);
         if (tid == 0) {
-            const double inv = n > 0 ? 1.0 / n : 0.0;
+            const double inv = n_used > 0 ? 1.0 / n_used : 0.0;
             double var = 0.0;
             for (int k = 0; k < 3; ++k) { s.cen[k] = s.fin[k] * inv; var += s.fin[3 + k] * inv - s.cen[k] * s.cen[k]; }
             s.scale = var > 0.0 ? sqrt(var / 3.0) : 1.0;
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kInitNT) lc_init_kernel(const lc_init_args d) 
         const bool robust = round > 0;
         double R[9], t[3];
         if (robust) { for (int k = 0; k < 9; ++k) R[k] = s.R[k]; for (int k = 0; k < 3; ++k) t[k] = s.t[k]; }
-        for (int i = tid; i < n; i += kInitNT) {
+        for (int i = tid * step; i < n; i += kInitNT * step) {
             const double X0 = X[i * Xn], X1 = X[i * Xn + Xc], X2 = X[i * Xn + 2 * Xc];
             const double u = x[i * xn], v = x[i * xn + xc];
             double wt = w ? 0.5 * (static_cast<double>(w[i * wn]) + static_cast<double>(w[i * wn + wc])) : 1.0;

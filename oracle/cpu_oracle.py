@@ -410,16 +410,21 @@ def select_pose(mode, cam_K, pts_a, pts_b, pose_candi):
 # ------------------------------------------------------------------------------------------------
 # Device-side initialiser: numpy restatement of lc_init.cu (our algorithm; the reference uses OpenCV)
 # ------------------------------------------------------------------------------------------------
-def pnp_init(K, pts3d, pts2d, weights=None, reproj_thresh=3.0, irls_rounds=3):
+def pnp_init(K, pts3d, pts2d, weights=None, reproj_thresh=3.0, irls_rounds=3, max_points=1024):
     """Weighted DLT reduced to a 4x4 eigenproblem + Cauchy IRLS, one pose.  K (3,3), pts3d (n,3), pts2d (n,2), weights (n,2)
     inverse variances or None.  Returns (ok, R (3,3), t (3,), inlier (n,) bool).  Same steps and formulas as lc_init.cu."""
     K, X, x = np.asarray(K, np.float64), np.asarray(pts3d, np.float64), np.asarray(pts2d, np.float64)
     n = len(X)
+    n_all = n
     if n < 6:
-        return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+        return False, np.eye(3), np.zeros(3), np.zeros(n_all, bool)
     base = np.ones(n) if weights is None else 0.5 * np.asarray(weights, np.float64).sum(1)
     base = np.where((base > 0) & np.isfinite(base), base, 0.0)
     Ki = np.linalg.inv(K)
+    X_all, x_all = X, x
+    step = -(-n // max_points) if n > max_points else 1            # the sums use every step-th correspondence (lc_init.cu)
+    X, x, base = X[::step], x[::step], base[::step]
+    n = len(X)
     cen = X.mean(0)
     var = (X * X).mean(0) - cen * cen
     sc = np.sqrt(var.sum() / 3.0) if var.sum() > 0 else 1.0
@@ -448,17 +453,17 @@ def pnp_init(K, pts3d, pts2d, weights=None, reproj_thresh=3.0, irls_rounds=3):
         try:
             np.linalg.cholesky(S)
         except np.linalg.LinAlgError:
-            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+            return False, np.eye(3), np.zeros(3), np.zeros(n_all, bool)
         Zx, Zy = np.linalg.solve(S, Sx), np.linalg.solve(S, Sy)
         D = Sq - Sx @ Zx - Sy @ Zy
         D = 0.5 * (D + D.T)
         tr = np.trace(D)
         if not (tr > 0):
-            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+            return False, np.eye(3), np.zeros(3), np.zeros(n_all, bool)
         try:
             Lc = np.linalg.cholesky(D + 1e-12 * tr * np.eye(4))      # inverse iteration, as lc_init.cu::sym4_min_eigvec
         except np.linalg.LinAlgError:
-            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+            return False, np.eye(3), np.zeros(3), np.zeros(n_all, bool)
         p3 = np.array([0.1, 0.1, 0.1, 1.0])
         for _ in range(5):
             p3 = np.linalg.solve(Lc.T, np.linalg.solve(Lc, p3))
@@ -475,6 +480,7 @@ def pnp_init(K, pts3d, pts2d, weights=None, reproj_thresh=3.0, irls_rounds=3):
         R = np.stack((r1, r2, np.cross(r1, r2)))
         t = Q[:, 3] / lam
         if not (np.isfinite(R).all() and np.isfinite(t).all() and lam > 0):
-            return False, np.eye(3), np.zeros(3), np.zeros(n, bool)
+            return False, np.eye(3), np.zeros(3), np.zeros(n_all, bool)
+    X, x = X_all, x_all                                            # the inlier mask covers every correspondence
     e2, h2 = reproj_err2(R, t)
     return True, R, t, (h2 > 0) & (e2 < reproj_thresh ** 2)
