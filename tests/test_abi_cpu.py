@@ -92,6 +92,48 @@ def test_operators_refuse_cpu_tensors():
         pnp_auto.weighted_pnp_jac_wrt_pts2d(c.pts2d, c.pose, c.K, c.pts3d, c.inv_std ** 2)
 
 
+def test_row_operators_refuse_cpu_tensors_and_validate_arguments():
+    """Rows f1-f4: same rule (no fallback), and the C ABI rejects malformed argument structs before touching a device."""
+    from lc_b200.dense import dense_pose_loss, dense_pose_loss_noc_bin
+    from lc_b200.floatbits import nn_out_to_xyz, nn_noc2target
+    from lc_b200.select import dense_point_select
+    from lc_b200.pnp import init_solver
+    from lc_b200.evaluate import compute_pose_errors
+    from lc_b200.symmetry import select_pose_2d
+    from lc_b200.synth import make_dense_outputs, make_zebra_outputs, make_correspondences
+    d = make_dense_outputs(2, 8, 8, 0)
+    z = make_zebra_outputs(2, 8, 8, 0, (3, 3, 3))
+    c = make_correspondences(2, 8, 0).to(torch.float32)
+    calls = [
+        lambda: dense_pose_loss(d["xyz_noc"], d["logits"], d["scale"], d["noc_scale"], d["K"], d["pose"], d["bbox_3d"], top_left=(0, 0)),
+        lambda: dense_pose_loss_noc_bin(z["bin_logits"], z["raw_bits"], z["logits"], z["scale"], z["msk_noc"], z["noc_scale"], z["K"], z["pose"],
+                                        z["bbox_3d"], bit_cnt=3, top_left=(0, 0)),
+        lambda: nn_out_to_xyz(z["bin_logits"], z["noc_scale"], bit_cnt=3),
+        lambda: nn_noc2target(torch.zeros(1, 4, 4, 3), 3),
+        lambda: dense_point_select(torch.zeros(1, 8, 8, 3), torch.zeros(1, 1, 8, 8), xyz_weights=torch.ones(1, 2, 8, 8)),
+        lambda: init_solver.solve(c.K, c.pts3d, c.pts2d),
+        lambda: compute_pose_errors(torch.eye(3)[None].double(), torch.zeros(1, 3).double(), torch.eye(3)[None].double(),
+                                    torch.zeros(1, 3).double(), torch.zeros(5, 3).double()),
+        lambda: select_pose_2d(c.K, c.pts3d, c.pts2d, torch.zeros(2, 3, 3, 4)),
+    ]
+    for fn in calls:
+        with pytest.raises(nat.NativeLibraryError):
+            fn()
+    handle = nat.lib()
+    for name, ty in (("lc_b200_dense_loss_fwd_bwd", nat.lc_dense_args), ("lc_b200_noc_bin_decode", nat.lc_decode_args),
+                     ("lc_b200_noc_bin_encode", nat.lc_encode_args), ("lc_b200_dense_select", nat.lc_select_args),
+                     ("lc_b200_pnp_init", nat.lc_init_args), ("lc_b200_pose_errors", nat.lc_eval_args),
+                     ("lc_b200_select_pose", nat.lc_candi_args)):
+        a = ty()
+        assert getattr(handle, name)(None, None) < 0                      # NULL struct
+        assert getattr(handle, name)(ctypes.byref(a), None) < 0           # abi_version 0
+        assert b"abi_version" in handle.lc_b200_last_error()
+        a.abi_version = nat.ABI_VERSION
+        a.B = 1
+        assert getattr(handle, name)(ctypes.byref(a), None) < 0           # sizes / required pointers missing
+    assert len(_declared_symbols()) == len(nat.EXPORTS) == 15
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "lc_b200")):
         for f in files:
