@@ -26,7 +26,17 @@ struct LmState {
     double cost, radius, dec, xnorm, gmax, model_change, reported_radius;
     double Rm[9], Jl[9], te[3];  // rotation, left Jacobian and translation of the evaluation point
     int reuse_diag, n_invalid, it, step_ok, any_success, ctl, term, pad;
+#ifdef LC_TIMING
+    long long tm[6], tm0;        // cycles inside lm_advance: normal equations, Cholesky solve, model change, eval point, rest
+#endif
 };
+#ifdef LC_TIMING
+#define LM_T0() L.tm0 = clock64()
+#define LM_T(k) do { const long long t_ = clock64(); L.tm[k] += t_ - L.tm0; L.tm0 = t_; } while (0)
+#else
+#define LM_T0() do {} while (0)
+#define LM_T(k) do {} while (0)
+#endif
 
 struct PoseShared {
     double K[9], pose[7], R[9], Rb[9], t[3], bbox[24];
@@ -214,6 +224,7 @@ __device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool 
                                   bool tol_guard, double* trace) {
     const double gtol = 1e-10, ptol = 1e-8, min_rel_dec = 1e-3;
     const double min_radius = 1e-32, max_radius = 1e16, min_diag = 1e-6, max_diag = 1e32;
+    LM_T0();
     if (first) {
         L.radius = 1e4; L.dec = 2.0; L.reuse_diag = 0; L.n_invalid = 0; L.it = 0; L.any_success = 0;
         L.reported_radius = L.radius; L.term = TERM_FAILURE; L.model_change = 0.0;
@@ -244,6 +255,7 @@ __device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool 
             L.radius = L.radius / L.dec; L.dec *= 2.0; L.reuse_diag = 1; L.step_ok = 0;
         }
     }
+    LM_T(0);
     for (;;) {
         // FinalizeIterationAndCheckIfMinimizerCanContinue
         L.reported_radius = L.radius;
@@ -261,7 +273,9 @@ __device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool 
         const double inv_radius = fast_rcp(L.radius);
 #pragma unroll
         for (int k = 0; k < 6; ++k) dd[k] = L.diag[k] * inv_radius;
+        LM_T(4);
         bool valid = chol6_solve_packed(L.A, dd, L.gs, y);
+        LM_T(1);
         L.reuse_diag = 1;
         double mc = 0.0;
         if (valid) {
@@ -287,11 +301,13 @@ __device__ inline void lm_advance(LmState& L, const double* fin, int kind, bool 
             L.radius *= 0.5; L.reuse_diag = 1; L.step_ok = 0;  // StepIsInvalid
             continue;
         }
+        LM_T(2);
         L.n_invalid = 0;
         L.model_change = mc;
 #pragma unroll
         for (int k = 0; k < 6; ++k) L.xc[k] = L.x[k] + y[k] * L.scale[k];
         lm_set_eval_point(L, L.xc);
+        LM_T(3);
         const bool armed_next = !tol_guard || L.any_success;
         L.ctl = (armed_next && mc <= 2.0 * ftol * L.cost) ? CTL_EVAL_COST : CTL_EVAL_FULL;
         return;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
     if (n > n_max) return;   // ragged batch split by n_points: this pose belongs to the streaming launch (lc_abi.cu)
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
 #ifdef LC_TIMING
-    if (tid == 0) for (int k = 0; k < 8; ++k) s.fin_timing[k] = 0;
+    if (tid == 0) { for (int k = 0; k < 8; ++k) s.fin_timing[k] = 0; for (int k = 0; k < 6; ++k) s.lm.tm[k] = 0; }
     const long long t_begin = clock64();
 #endif
     { LC_TIC(tq1);
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
     }
 #ifdef LC_TIMING
     if (!(MODE & MODE_LC)) {
-        if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin); }
+        if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
+            for (int k = 0; k < 6; ++k) tr[48 + k] = (double)s.lm.tm[k]; }
         return;
     }
 #else

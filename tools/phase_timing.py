@@ -56,6 +56,9 @@ def run(pipeline):
     print(f"{pipeline}: mean cycles per pose (thread 0), iters mean {it.float().mean().item() if pipeline != 'p1' else 0:.2f}")
     for k, nme in enumerate(names):
         print(f"  {nme:12s} {t[:, k].mean():10.0f}  {100 * t[:, k].mean() / tot:5.1f}%")
+    if pipeline == "p2":
+        m = trace.reshape(B, -1)[:, 48:54].cpu().numpy().mean(0)
+        print("  inside lm_advance (cycles per pose): normal eq %.0f, Cholesky solve %.0f, model change %.0f, eval point %.0f, rest %.0f" % tuple(m[:5]))
     if pipeline == "p1":
         m = trace.reshape(B, -1)[:, 8:48].cpu().numpy().mean(0)
         print("  6x6 section barrier marks (cycles since entry):", " ".join(f"{v:.0f}" for v in m if v > 0))
