@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) lc_dense_kernel(const lc_dense_a
     // ---- LC loss forward + per-point gradients ----
     const SoftmaxWeights wsrc{lg, lg + lgc, g, m, kk};
     DenseSink sink{l, 0.f, d.g_xyz_noc.ptr || d.g_logits.ptr || d.g_scale.ptr || (ZEBRA && d.g_noc_bin.ptr)};
-    lc_phase_res<NT>(a, s, l, b, n, wsrc, sink);
+    lc_phase_res<NT>(a, s, l, b, n, wsrc, sink, XAcc<false>{l, 0u});
     if (!sink.want) return;
 
     // ---- epilogue: softmax backward and the scatter, every pixel written once ----

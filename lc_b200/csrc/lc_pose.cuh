@@ -51,6 +51,7 @@ struct PoseShared {
     double cHL[kSym], cGL[kSym], bL[6];  // reverse-pass coefficients, left basis, packed (off-diagonals doubled)
     int flag, pad;
     unsigned long long tma_bar;  // mbarrier of the TMA staging (lc_resident.cu)
+    unsigned tmem_base, tmem_pad;  // tensor-memory allocation of TM kernels (lc_resident.cu)
 #ifdef LC_TIMING
     long long fin_timing[8];     // cycles per phase (thread 0): stage, lm pass, lm advance, lc setup, lc passes 1-3, six, pass 4
     long long marks[48];         // clock64() at the barriers of the 6x6 sections (LC_MARK)

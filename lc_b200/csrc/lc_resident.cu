@@ -23,16 +23,37 @@
 
 namespace lc {
 
-template <int NT, int MODE>
+// TM = true: the model points live in tensor memory (lc_resident.cuh: XAcc), shared memory holds only x -> ec.
+template <int NT, int MODE, bool TM>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask, int n_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
-    const ResLayout l = res_layout(smem_raw, npad);
+    const ResLayout l = TM ? res_layout_tm(smem_raw, npad) : res_layout(smem_raw, npad);
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
     if (n > n_max) return;   // ragged batch split by n_points: this pose belongs to the streaming launch (lc_abi.cu)
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
+    uint32_t tb = 0;
+    if (TM) {
+        // kTmemCols columns of tensor memory for this CTA (4 CTAs x 128 = all 512 columns of the SM); a CTA that finds
+        // none free waits inside tcgen05.alloc until a resident CTA releases its columns
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tb = s.tmem_base + ((static_cast<uint32_t>(tid >> 5) & 3u) * 32u << 16);
+    }
+    auto tmem_release = [&]() {
+        if (TM) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem_base), "n"(kTmemCols) : "memory");
+        }
+    };
 #ifdef LC_TIMING
     if (tid == 0) { for (int k = 0; k < 8; ++k) s.fin_timing[k] = 0; for (int k = 0; k < 6; ++k) s.lm.tm[k] = 0; }
     const long long t_begin = clock64();
@@ -47,7 +68,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
         const float* p3 = static_cast<const float*>(a.pts3d.ptr) + b * a.pts3d.stride[0];
         const float* p2 = static_cast<const float*>(a.pts2d.ptr) + b * a.pts2d.stride[0];
         const int64_t s3n = a.pts3d.stride[1], s3c = a.pts3d.stride[2], s2n = a.pts2d.stride[1], s2c = a.pts2d.stride[2];
-        const bool tma3 = (tma_mask & 1) != 0, tma2 = (tma_mask & 2) != 0;
+        const bool tma3 = !TM && (tma_mask & 1) != 0, tma2 = (tma_mask & 2) != 0;
         if (tma_mask) {
             if (tid == 0) mbar_init(&s.tma_bar, 1);
             __syncthreads();
@@ -66,13 +87,34 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
         if (!(tma3 && tma2)) {
             for (int i = tid; i < npad; i += NT) {
                 if (i < n) {
-                    if (!tma3) { cp_async4(l.A0 + i, p3 + i * s3n); cp_async4(l.A1 + i, p3 + i * s3n + s3c); cp_async4(l.A2 + i, p3 + i * s3n + 2 * s3c); }
+                    if (!TM && !tma3) { cp_async4(l.A0 + i, p3 + i * s3n); cp_async4(l.A1 + i, p3 + i * s3n + s3c); cp_async4(l.A2 + i, p3 + i * s3n + 2 * s3c); }
                     if (!tma2) { cp_async4(l.B0 + i, p2 + i * s2n); cp_async4(l.B1 + i, p2 + i * s2n + s2c); }
                 } else {
-                    if (!tma3) { l.A0[i] = 0.f; l.A1[i] = 0.f; l.A2[i] = 0.f; }
+                    if (!TM && !tma3) { l.A0[i] = 0.f; l.A1[i] = 0.f; l.A2[i] = 0.f; }
                     if (!tma2) { l.B0[i] = 0.f; l.B1[i] = 0.f; }
                 }
             }
+        }
+        if (TM) {
+            // model points: global -> registers -> the thread's TMEM lane, eight points (24 loads) in flight per thread
+            const int wbase = tid & ~31;
+            for (int k0 = 0; k0 * NT + wbase < n; k0 += 8) {
+                float v[8][3];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = tid + (k0 + j) * NT;
+                    const bool live = i < n;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float x = live ? p3[i * s3n + c * s3c] : 0.f;
+                        v[j][c] = sanitize ? nan_to_num_f(x) : x;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if ((k0 + j) * NT + wbase < n) tmem_st4(tb + 4u * (k0 + j), v[j][0], v[j][1], v[j][2], 0.f);   // warp-uniform predicate
+            }
+            tmem_wait_st();
         }
     }
     // ---- pose constants ----
@@ -92,12 +134,13 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
     if (sanitize) {
         // solver prologue on the thread's own elements: nan_to_num (cer_solver.py:27-29)
         for (int i = tid; i < n; i += NT) {
-            l.A0[i] = nan_to_num_f(l.A0[i]); l.A1[i] = nan_to_num_f(l.A1[i]); l.A2[i] = nan_to_num_f(l.A2[i]);
+            if (!TM) { l.A0[i] = nan_to_num_f(l.A0[i]); l.A1[i] = nan_to_num_f(l.A1[i]); l.A2[i] = nan_to_num_f(l.A2[i]); }
             l.B0[i] = nan_to_num_f(l.B0[i]); l.B1[i] = nan_to_num_f(l.B1[i]);
         }
     }
     __syncthreads();
     LC_TOC(tq1, 0); }
+    const XAcc<TM> xs{l, tb};
 
     // =========================== LM solve (fp64) ===========================
     if (MODE & MODE_LM) {
@@ -120,8 +163,8 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             for (;;) {
                 const int kind = L.ctl;
                 { LC_TIC(tq2);
-                if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(a, s, l, b, n, sanitize);
-                else lm_eval_pass_res<NT, true>(a, s, l, b, n, sanitize);
+                if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(a, s, l, b, n, sanitize, xs);
+                else lm_eval_pass_res<NT, true>(a, s, l, b, n, sanitize, xs);
                 LC_TOC(tq2, 1); }
                 LC_TIC(tq3);
                 if (tid == 0)
@@ -140,16 +183,18 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
     if (!(MODE & MODE_LC)) {
         if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
             for (int k = 0; k < 6; ++k) tr[48 + k] = (double)s.lm.tm[k]; }
+        tmem_release();
         return;
     }
 #else
-    if (!(MODE & MODE_LC)) return;
+    if (!(MODE & MODE_LC)) { tmem_release(); return; }
 #endif
 
     // =========================== LC loss ===========================
     const DirectWeights wsrc{static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0], a.weights.stride[1], a.weights.stride[2]};
     DirectSink sink{a, b};
-    lc_phase_res<NT>(a, s, l, b, n, wsrc, sink);
+    lc_phase_res<NT>(a, s, l, b, n, wsrc, sink, xs);
+    tmem_release();
 #ifdef LC_TIMING
     if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
         for (int k = 0; k < 40; ++k) tr[8 + k] = (double)(s.marks[k] - s.marks[0]); }
@@ -202,26 +247,35 @@ static int tma_mask_for(const lc_args& a) {
     return m | ((m && w_planar && !getenv("LC_B200_NO_L2PF")) ? 4 : 0);
 }
 
-template <int NT, int MODE>
+template <int NT, int MODE, bool TM = false>
 static int launch_res_t(const lc_args& a, cudaStream_t st, int cap) {
-    const int n_res = cap > 0 ? cap : a.N;   // points held in shared memory per pose
-    const size_t smem = resident_smem_bytes(n_res);
+    const int n_res = cap > 0 ? cap : a.N;   // points held on chip per pose
+    const size_t smem = TM ? resident_smem_bytes_tm(n_res) : resident_smem_bytes(n_res);
     static bool configured[64] = {};   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
+        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
         if (e != cudaSuccess) return static_cast<int>(e);
         configured[dev] = true;
     }
-    lc_resident_kernel<NT, MODE><<<a.B, NT, smem, st>>>(a, round_up4(n_res), tma_mask_for(a), cap > 0 ? cap : 0x7fffffff);
+    lc_resident_kernel<NT, MODE, TM><<<a.B, NT, smem, st>>>(a, round_up4(n_res), tma_mask_for(a), cap > 0 ? cap : 0x7fffffff);
     return static_cast<int>(cudaGetLastError());
+}
+
+// Which modes take the tensor-memory variant (measured on B200 at B = 1024 x N = 4096, see profiles/README.md): the loss-only
+// kernel gains from four finer-grained CTAs per SM; LC_B200_TMEM = 0 | 1 | lc overrides for A/B runs.
+static bool tmem_enabled(int mode) {
+    if (const char* e = getenv("LC_B200_TMEM")) return e[0] == '1' || (e[0] == 'l' && mode == MODE_LC);
+    return mode == MODE_LC;
 }
 
 template <int MODE>
 static int launch_res_m(const lc_args& a, cudaStream_t st, int cap) {
     // 256 threads x 2 CTAs per SM (20 B/point of shared memory): one CTA's 6x6 / trust-region sections and loads
     // overlap the other CTA's point passes
+    // 2048 < N <= 4096: four 128-thread CTAs per SM with the model points in tensor memory (lc_resident.cuh: XAcc)
+    if (cap == 0 && a.N > 2048 && a.N <= kTmemMaxN && tmem_enabled(MODE)) return launch_res_t<128, MODE, true>(a, st, cap);
     const int nt = resident_threads_for(cap > 0 ? cap : a.N, MODE);
     if (nt == 128) return launch_res_t<128, MODE>(a, st, cap);
     if (nt == 192) return launch_res_t<192, MODE>(a, st, cap);

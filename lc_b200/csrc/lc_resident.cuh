@@ -36,6 +36,17 @@ __device__ __forceinline__ ResLayout res_layout(unsigned char* base, int npad) {
     return l;
 }
 
+// TM kernels: only x -> ec lives in shared memory (8 B/point)
+__device__ __forceinline__ ResLayout res_layout_tm(unsigned char* base, int npad) {
+    float* f = reinterpret_cast<float*>(base + ((sizeof(PoseShared) + 15) & ~size_t(15)));
+    ResLayout l;
+    l.A0 = nullptr; l.A1 = nullptr; l.A2 = nullptr; l.B0 = f; l.B1 = f + npad;
+    return l;
+}
+inline size_t resident_smem_bytes_tm(int n) {
+    return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * 2 * static_cast<size_t>(round_up4(n));
+}
+
 inline size_t resident_smem_bytes(int n) {
     return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * 5 * static_cast<size_t>(round_up4(n));
 }
@@ -86,10 +97,49 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
     }
 }
 
+// ---- tensor memory (TMEM) as per-thread scratch ----
+// The 256 KB of tensor memory per SM are otherwise unused by this path.  Every thread only ever touches its own points
+// (i = tid + k NT), so the per-point 3-vector (X, later q = R X) can live in the thread's own TMEM lane, 4 columns per point
+// (tcgen05.st / tcgen05.ld 32x32b.x4), while only x -> ec (8 B/point) stays in shared memory: 47 KB per CTA at N = 4096, i.e.
+// four 128-thread CTAs per SM where shared memory alone allows two 256-thread ones.  tools/tmem_probe.cu checks the idiom.
+__device__ __forceinline__ void tmem_st4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+                 "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t addr, float& a, float& b, float& c) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    a = __uint_as_float(r0); b = __uint_as_float(r1); c = __uint_as_float(r2);
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr int kTmemCols = 128;           // columns per CTA: 32 points per thread x 4
+constexpr int kTmemMaxN = 128 * 32;      // with 128 threads
+
+// Where the per-point 3-vector lives.  TM = false: planar shared-memory arrays (any N that fits).  TM = true: the thread's
+// TMEM lane; loads / stores are warp-collective (.sync.aligned), so the point loops of TM kernels run to a warp-uniform
+// bound with a `live` predicate (see LC_POINT_LOOP).
+template <bool TM>
+struct XAcc {
+    ResLayout l;
+    uint32_t tb;   // TMEM address of this warp's lane quarter (TM only)
+    __device__ __forceinline__ void ld(int i, int k, bool live, float& a, float& b, float& c) const {
+        if (TM) tmem_ld4(tb + 4u * k, a, b, c);
+        else if (live) { a = l.A0[i]; b = l.A1[i]; c = l.A2[i]; }
+    }
+    __device__ __forceinline__ void st(int i, int k, bool live, float a, float b, float c) const {
+        if (TM) tmem_st4(tb + 4u * k, a, b, c, 0.f);
+        else if (live) { l.A0[i] = a; l.A1[i] = b; l.A2[i] = c; }
+    }
+};
+// for (point i of this thread, k-th of them): TM kernels iterate to a warp-uniform bound, `live` masks the tail
+#define LC_POINT_LOOP(TM, NT, n)                                                                                   \
+    for (int i = threadIdx.x, k = 0; ((TM) ? (k * (NT) + static_cast<int>(threadIdx.x & ~31u)) : i) < (n); i += (NT), ++k)
+
 // One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
 // staged fp32 arrays: cost, and when JAC also J'^T J' and J'^T r in the left basis.
-template <int NT, bool JAC>
-__device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
+template <int NT, bool JAC, bool TM>
+__device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize, const XAcc<TM>& xs) {
     const LmState& L = s.lm;
     double acc[28];
 #pragma unroll
@@ -103,10 +153,13 @@ __device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s
     const float* pw = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
     const int64_t swn = a.weights.stride[1], swc = a.weights.stride[2];
     const bool icov = a.weight_mode == LC_W_ICOV_DIAG;
-    int i = threadIdx.x;
     float w0 = 0.f, w1 = 0.f;
-    if (i < n) { w0 = pw[i * swn]; w1 = pw[i * swn + swc]; }
-    for (; i < n; i += NT) {
+    if (static_cast<int>(threadIdx.x) < n) { w0 = pw[threadIdx.x * swn]; w1 = pw[threadIdx.x * swn + swc]; }
+    LC_POINT_LOOP(TM, NT, n) {
+        const bool live = !TM || i < n;
+        float Xf0 = 0.f, Xf1 = 0.f, Xf2 = 0.f;
+        xs.ld(i, k, live, Xf0, Xf1, Xf2);
+        if (!live) continue;
         float wa = w0, wb = w1;
         const int inext = i + NT;
         if (inext < n) { w0 = pw[inext * swn]; w1 = pw[inext * swn + swc]; }
@@ -115,7 +168,7 @@ __device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s
         // |s| (barring overflow / underflow of s*s).
         if (icov) { wa = sqrtf(wa); wb = sqrtf(wb); }
         const double la = fabsf(wa), lc_ = fabsf(wb);
-        const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i];
+        const double X0 = Xf0, X1 = Xf1, X2 = Xf2;
         const double px = l.B0[i], py = l.B1[i];
         const double q0 = fma(R0, X0, fma(R1, X1, R2 * X2));
         const double q1 = fma(R3, X0, fma(R4, X1, R5 * X2));
@@ -175,8 +228,9 @@ struct DirectSink {      // gradients written to the strided views of lc_args
     }
 };
 
-template <int NT, class WSrc, class Sink>
-__device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, const WSrc& wsrc, Sink& sink) {
+template <int NT, class WSrc, class Sink, bool TM>
+__device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, const WSrc& wsrc, Sink& sink,
+                                             const XAcc<TM>& xs) {
     const int tid = threadIdx.x;
     { LC_TIC(tq1);
     if (tid == 0) { lc_pose_setup(s, true); lc_pose_setup_acc(s); }
@@ -190,8 +244,13 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
         const double Lmax = a.max_err_len;
         const double lim = Lmax - 1e-6, lim2 = lim > 0.0 ? lim * lim : -1.0;   // |e|+1e-6 > Lmax  <=>  |e|^2 > lim2
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-        for (int i = tid; i < n; i += NT) {
-            const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i], x0 = l.B0[i], x1 = l.B1[i];
+        LC_POINT_LOOP(TM, NT, n) {
+            const bool live = !TM || i < n;
+            float Xf0 = 0.f, Xf1 = 0.f, Xf2 = 0.f;
+            xs.ld(i, k, live, Xf0, Xf1, Xf2);
+            float qf0 = 0.f, qf1 = 0.f, qf2 = 0.f;
+            if (live) {
+            const double X0 = Xf0, X1 = Xf1, X2 = Xf2, x0 = l.B0[i], x1 = l.B1[i];
             const double q0 = fma(s.R[0], X0, fma(s.R[1], X1, s.R[2] * X2));
             const double q1 = fma(s.R[3], X0, fma(s.R[4], X1, s.R[5] * X2));
             const double q2 = fma(s.R[6], X0, fma(s.R[7], X1, s.R[8] * X2));
@@ -210,11 +269,14 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
             }
             const float ec0 = static_cast<float>(e0), ec1 = static_cast<float>(e1);
             // q = R X is what is cached (not P = q + t): q x D then keeps fp32 relative precision even when |X| << |t|
-            l.A0[i] = static_cast<float>(q0); l.A1[i] = static_cast<float>(q1); l.A2[i] = static_cast<float>(q2);
+            qf0 = static_cast<float>(q0); qf1 = static_cast<float>(q1); qf2 = static_cast<float>(q2);
             l.B0[i] = ec0; l.B1[i] = ec1;
             const float v = a.valid.ptr ? ldf(a.valid, ovb + i * a.valid.stride[1]) : 1.f;
             acc0 = fmaf(v, fabsf(ec0), acc0); acc1 = fmaf(v, fabsf(ec1), acc1); acc2 += v;
+            }
+            xs.st(i, k, live, qf0, qf1, qf2);
         }
+        if (TM) tmem_wait_st();
         double acc[3] = {acc0, acc1, acc2};
         block_reduce<3, NT>(acc, s.red, s.fin);
     }
@@ -252,8 +314,8 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
     const float uc = static_cast<float>(s.t[0] / s.t[2]), vc = static_cast<float>(s.t[1] / s.t[2]);
 
     // per-point fp32 geometry shared by passes 3 and 4: left-basis Jacobian rows and robust weights
-    auto point_terms = [&](int i, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2], float (&w)[2]) {
-        const float q0 = l.A0[i], q1 = l.A1[i], q2 = l.A2[i];
+    auto point_terms = [&](int i, float q0, float q1, float q2, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2],
+                           float (&w)[2]) {
         const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
         ec[0] = l.B0[i]; ec[1] = l.B1[i];
         wsrc.get(i, sk[0], sk[1]);
@@ -281,9 +343,13 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
         float acc[48];
 #pragma unroll
         for (int k = 0; k < 48; ++k) acc[k] = 0.f;
-        for (int i = tid; i < n; i += NT) {
+        LC_POINT_LOOP(TM, NT, n) {
+            const bool live = !TM || i < n;
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+            xs.ld(i, k, live, q0, q1, q2);
+            if (!live) continue;
             float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
-            point_terms(i, J, ec, sk, sg, del, w);
+            point_terms(i, q0, q1, q2, J, ec, sk, sg, del, w);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 acc_outer<0>(acc, w[c], J[c]);
@@ -319,9 +385,13 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
         float Rf[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
-        for (int i = tid; i < n; i += NT) {
+        LC_POINT_LOOP(TM, NT, n) {
+            const bool live = !TM || i < n;
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+            xs.ld(i, k, live, q0, q1, q2);
+            if (!live) continue;
             float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
-            point_terms(i, J, ec, sk, sg, del, w);
+            point_terms(i, q0, q1, q2, J, ec, sk, sg, del, w);
             float ecb[2];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -349,7 +419,7 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
             }
             if (sink.want_pts3d()) {
                 // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
-                const float P0 = l.A0[i] + t0, P1 = l.A1[i] + t1, P2 = l.A2[i] + t2;
+                const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
                 const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
                 const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
                 const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
