@@ -24,6 +24,10 @@
 namespace lc {
 
 // TM = true: the model points live in tensor memory (lc_resident.cuh: XAcc), shared memory holds only x -> ec.
+#ifdef LC_TIMING
+__device__ int g_live_ctas[256];   // CTAs currently resident per SM (tools/phase_timing.py: measured concurrency)
+#endif
+
 template <int NT, int MODE, bool TM>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask, int n_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -57,6 +61,10 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
 #ifdef LC_TIMING
     if (tid == 0) { for (int k = 0; k < 8; ++k) s.fin_timing[k] = 0; for (int k = 0; k < 6; ++k) s.lm.tm[k] = 0; }
     const long long t_begin = clock64();
+    unsigned smid_;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid_));
+    int live_at_start = 0;
+    if (tid == 0) live_at_start = atomicAdd(&g_live_ctas[smid_], 1) + 1;
 #endif
     { LC_TIC(tq1);
 
@@ -96,12 +104,12 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             }
         }
         if (TM) {
-            // model points: global -> registers -> the thread's TMEM lane, eight points (24 loads) in flight per thread
+            // model points: global -> registers -> the thread's TMEM lane, sixteen points (48 loads) in flight per thread
             const int wbase = tid & ~31;
-            for (int k0 = 0; k0 * NT + wbase < n; k0 += 8) {
-                float v[8][3];
+            for (int k0 = 0; k0 * NT + wbase < n; k0 += 16) {
+                float v[16][3];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const int i = tid + (k0 + j) * NT;
                     const bool live = i < n;
 #pragma unroll
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < 16; ++j)
                     if ((k0 + j) * NT + wbase < n) tmem_st4(tb + 4u * (k0 + j), v[j][0], v[j][1], v[j][2], 0.f);   // warp-uniform predicate
             }
             tmem_wait_st();
@@ -182,7 +190,8 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
 #ifdef LC_TIMING
     if (!(MODE & MODE_LC)) {
         if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
-            for (int k = 0; k < 6; ++k) tr[48 + k] = (double)s.lm.tm[k]; }
+            for (int k = 0; k < 6; ++k) tr[48 + k] = (double)s.lm.tm[k]; tr[60] = live_at_start; }
+        if (tid == 0) atomicAdd(&g_live_ctas[smid_], -1);
         tmem_release();
         return;
     }
@@ -197,7 +206,8 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
     tmem_release();
 #ifdef LC_TIMING
     if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
-        for (int k = 0; k < 40; ++k) tr[8 + k] = (double)(s.marks[k] - s.marks[0]); }
+        for (int k = 0; k < 40; ++k) tr[8 + k] = (double)(s.marks[k] - s.marks[0]); tr[60] = live_at_start; }
+    if (tid == 0) atomicAdd(&g_live_ctas[smid_], -1);
 #endif
 }
 

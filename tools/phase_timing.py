@@ -56,6 +56,8 @@ def run(pipeline):
     print(f"{pipeline}: mean cycles per pose (thread 0), iters mean {it.float().mean().item() if pipeline != 'p1' else 0:.2f}")
     for k, nme in enumerate(names):
         print(f"  {nme:12s} {t[:, k].mean():10.0f}  {100 * t[:, k].mean() / tot:5.1f}%")
+    lv = trace.reshape(B, -1)[:, 60].cpu().numpy()
+    print(f"  CTAs resident on the SM when a CTA starts (incl. itself): max {lv.max():.0f}, mean {lv.mean():.2f}")
     if pipeline == "p2":
         m = trace.reshape(B, -1)[:, 48:54].cpu().numpy().mean(0)
         print("  inside lm_advance (cycles per pose): normal eq %.0f, Cholesky solve %.0f, model change %.0f, eval point %.0f, rest %.0f" % tuple(m[:5]))
