@@ -203,3 +203,54 @@ def test_init_oracle_lands_in_the_same_lm_basin_as_opencv(oracle, tag):
     assert not ours["invalid"].any() and not cv["invalid"].any()
     assert quat_angle(ours["states"][:, :4].astype(np.float64), cv["states"][:, :4].astype(np.float64)).max() <= 1e-3
     assert (np.abs(ours["states"][:, 4:] - cv["states"][:, 4:]).max(1) <= 2e-3 * np.abs(cv["states"][:, 4:]).max(1)).all()
+
+
+def test_zebra_oracle_properties(oracle):
+    """Size-independent properties of the restated ZebraPose coding: (i) encode -> saturated logits -> training decode with the
+    GT bits returns the quantised coordinate inside the mask; (ii) a single wrong bit moves the decoded value by at most that
+    bit's weight and the gradient lands on exactly that bit; (iii) outside the mask the value is the hard decode, no gradient."""
+    rng = np.random.default_rng(0)
+    bits = (7, 6, 5)
+    noc = rng.uniform(-1.1, 1.1, (2, 6, 7, 3))
+    mod, raw = oracle.noc_to_bits(noc, bits)
+    logits = (mod.astype(np.float64) * 2 - 1) * 30.0
+    msk = np.ones((2, 6, 7), bool)
+    dec, sel, dnoc = oracle.noc_bin_decode_with_gt(logits, raw, msk, bits)
+    off = np.concatenate(([0], np.cumsum(bits)))
+    for a, N in enumerate(bits):
+        mx = 2 ** N - 1
+        q = np.rint(np.clip((noc[..., a] + 1) * (mx * 0.5), 0, mx))
+        # no wrong bit: the LSB is the soft one, sigmoid(+-30) restores it to 1e-13
+        assert np.abs(dec[..., a] - (q / (mx * 0.5) - 1)).max() <= 1e-12
+        assert (sel[..., a] == off[a] + N - 1).all()
+    # flip one mid bit of axis 0 at one pixel
+    l2 = logits.copy()
+    j = 2
+    l2[0, j, 3, 4] *= -1
+    dec2, sel2, dnoc2 = oracle.noc_bin_decode_with_gt(l2, raw, msk, bits)
+    assert sel2[0, 3, 4, 0] == j and abs(dec2[0, 3, 4, 0] - dec[0, 3, 4, 0]) <= 2 ** (bits[0] - 1 - j) / ((2 ** bits[0] - 1) * 0.5) + 1e-9
+    assert (sel2[..., 1:] == sel[..., 1:]).all()
+    # outside the mask: hard decode, zero gradient
+    msk0 = np.zeros_like(msk)
+    dec3, _, dnoc3 = oracle.noc_bin_decode_with_gt(l2, raw, msk0, bits)
+    assert (dnoc3 == 0).all()
+    hard = oracle.noc_bin_decode(logits, bits)
+    assert np.abs(oracle.noc_bin_decode_with_gt(logits, raw, msk0, bits)[0] - hard).max() <= 2.0 / (2 ** min(bits) - 1) + 1e-9
+
+
+def test_selection_oracle_properties(oracle):
+    """quantile rule keeps ceil-ish (1-q) of the points, 'quantile_in_mask' is a subset of the mask, 'mask' ignores weights."""
+    rng = np.random.default_rng(1)
+    B, H, W = 3, 20, 24
+    xyz = rng.normal(size=(B, H, W, 3)).astype(np.float32)
+    w = rng.uniform(0.1, 2.0, (B, 2, H, W)).astype(np.float32)
+    ml = rng.normal(size=(B, 1, H, W)).astype(np.float32)
+    for sample in (1, 2):
+        m = oracle.dense_point_select(xyz, w, ml, sample, "mask")
+        q = oracle.dense_point_select(xyz, w, ml, sample, "quantile", quantile=0.2)
+        qm = oracle.dense_point_select(xyz, w, ml, sample, "quantile_in_mask", quantile=0.2)
+        N = m["valid"].shape[1]
+        assert np.array_equal(m["valid"], (ml[:, 0, ::sample, ::sample] > 0).reshape(B, -1))
+        assert (np.abs(q["valid"].sum(1) - 0.8 * N) <= 2).all()
+        assert not (qm["valid"] & ~m["valid"]).any()
+        assert (np.abs(qm["valid"].sum(1) - 0.8 * m["valid"].sum(1)) <= 2).all()
