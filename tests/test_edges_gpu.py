@@ -120,3 +120,40 @@ def test_ragged_batch_padded_beyond_the_resident_limit_is_split_by_n_points(orac
                 state=torch.empty(B, 7, device="cuda"), invalid=torch.empty(B, dtype=torch.int32, device="cuda"),
                 weight_mode=nat.W_ICOV_DIAG, flags=nat.FLAG_TOL_NEEDS_SUCCESS)
     assert nat.call("lc_b200_lm_solve", nat.make_args(B, N, torch.float32, **args), d.K.device) == 2   # resident + streaming
+
+
+def test_loss_kernel_with_ragged_n_points_in_the_tensor_memory_range():
+    """N = 4096 takes the tensor-memory variant of the loss kernel (model points in TMEM, warp-uniform point loops with a
+    `live` predicate); ragged n_points must give what each pose gives alone on its trimmed tensors (shared-memory variant for
+    n <= 2048, streaming kernel for tiny n), and LC_B200_TMEM=0 must agree with the default."""
+    import os
+    from lc_b200 import _native as nat
+    from lc_b200.cov_mixed import loss_fwd_bwd
+    N = 4096
+    npts = [4096, 100, 3000, 2049, 33, 4095]
+    B = len(npts)
+    c = make_correspondences(B, N, 9).to(torch.float32).to(device="cuda")
+
+    def run():
+        loss = torch.empty(B, device="cuda")
+        g3, gs = torch.zeros(B, N, 3, device="cuda"), torch.zeros(B, N, 2, device="cuda")
+        a = nat.make_args(B, N, torch.float32, K=c.K, pose=c.pose, pts3d=c.pts3d, pts2d=c.pts2d, weights=c.inv_std, bbox=c.bbox_3d,
+                          n_points=torch.tensor(npts, dtype=torch.int32, device="cuda"), loss=loss, g_pts3d=g3, g_weights=gs)
+        nat.call("lc_b200_loss_fwd_bwd", a, c.K.device)
+        torch.cuda.synchronize()
+        return loss, g3, gs
+
+    loss, g3, gs = run()
+    for b, n in enumerate(npts):
+        o = loss_fwd_bwd(c.K[b:b + 1], c.pose[b:b + 1], c.pts3d[b:b + 1, :n].contiguous(), c.pts2d[b:b + 1, :n].contiguous(),
+                         c.inv_std[b:b + 1, :n].contiguous(), None, c.bbox_3d[b:b + 1])
+        assert abs(loss[b].item() - o["loss"][0].item()) <= 2e-6 * max(1.0, abs(o["loss"][0].item())), n
+        assert rel_err(g3[b:b + 1, :n].cpu().numpy(), o["g_pts3d"].cpu().numpy()) <= 2e-5, n
+        assert rel_err(gs[b:b + 1, :n].cpu().numpy(), o["g_inv_std"].cpu().numpy()) <= 2e-5, n
+        assert (g3[b, n:] == 0).all() and (gs[b, n:] == 0).all()          # slots beyond n_points are not touched
+    os.environ["LC_B200_TMEM"] = "0"
+    try:
+        loss0, g30, gs0 = run()
+    finally:
+        del os.environ["LC_B200_TMEM"]
+    assert torch.allclose(loss, loss0, rtol=2e-6) and rel_err(g3.cpu().numpy(), g30.cpu().numpy()) <= 2e-5
