@@ -9,7 +9,7 @@ from lc_b200.pnp.cer_solver import lm_solve
 from lc_b200.nll.pnp_auto import weighted_pnp_jac_wrt_pts2d
 from lc_b200 import _native as nat
 
-for (B, N) in [(3, 8), (2, 70), (2, 700), (2, 1300)]:
+for (B, N) in [(3, 8), (2, 70), (2, 700), (2, 1300), (2, 2500)]:   # 2500: tensor-memory variant of the loss kernel
     c = make_correspondences(B, N, 1).to(torch.float32).to(device="cuda")
     for stream in (False, True):
         loss_fwd_bwd(c.K, c.pose, planar_view(c.pts3d), c.pts2d, planar_view(c.inv_std), c.valid, c.bbox_3d, want_cov=True, force_streaming=stream)
