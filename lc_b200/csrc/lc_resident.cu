@@ -239,9 +239,13 @@ bool resident_supported(const lc_args& a, int mode) {
 // CTAs above.  Both give 16 warps/SM at 128 registers; the finer granularity hides the per-pose serial sections
 // better (measured on B200 at equal total points: N = 1024 P3 511 vs 651 us, N = 2048 389 vs 442 us; N = 2900, where
 // only three 128-thread CTAs fit, prefers 256).
-static int resident_threads_for(int n, int) {
+static int resident_threads_for(int n, int mode) {
     if (const char* e = getenv("LC_B200_RES_NT")) return atoi(e);   // tuning knob for benchmarks
-    return n <= 2048 ? 128 : 256;
+    if (n <= 2048) return 128;
+    // solve-only: 192 threads x 164 registers keep the 28 fp64 accumulators + pose constants of the LM pass out of local
+    // memory (the 256-thread build spills 8 of them); 12 warps/SM are enough for the fp64-pipe-bound pass (P2 196 -> 189 us).
+    // The loss passes are issue-bound and want the 16 warps (P1 +18 %, P3 +6 % with 192).
+    return mode == MODE_LM ? 192 : 256;
 }
 
 // A (B,N,C) fp32 view can be staged by 1-D TMA bulk copies when every component slab is contiguous (point stride 1)
