@@ -384,7 +384,7 @@ def main():
     bytes_per_launch = B * algorithmic_bytes_per_pose(a.pipeline, N)
     launch_s = ms * 1e-3 / a.steps
     achieved = bytes_per_launch / launch_s / 1e9
-    kernel = {"p3": "lc::lc_resident_kernel<256, LM|LC>", "p1": "lc::lc_resident_kernel<128, LC, TMEM> (model points in tensor memory, 4 CTAs/SM)", "p2": "lc::lc_resident_kernel<256, LM>"}[a.pipeline]
+    kernel = {"p3": "lc::lc_resident_kernel<256, LM|LC>", "p1": "lc::lc_resident_kernel<128, LC, TMEM> (model points in tensor memory, 4 CTAs/SM)", "p2": "lc::lc_resident_kernel<192, LM>"}[a.pipeline]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(a.pipeline), "kernel": kernel, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "launch_us": launch_s * 1e6,
