@@ -302,6 +302,28 @@ int lc_b200_pnp_jac_cov_bwd(const lc_args* a, void* cuda_stream);
 
 /* number of kernels the last call on this thread launched (bench.py's gpu_launches claim) */
 int lc_b200_last_launch_count(void);
+/* names of those kernels (template instantiations as dispatched), '+'-separated; valid until the next call on this thread */
+const char* lc_b200_last_kernels(void);
+
+/*
+ * Binary-compatible replacement of the symbol the reference's cffi module binds (lib/pnp/cxx/ext.h:1-14, implemented in
+ * lib/pnp/cxx/ceres.cpp:147-177 and called from lib/pnp/pnp_ceres.py:136-139): same name, same argument list, HOST pointer
+ * tables with one ragged job per entry (float[7] wxyz+t in/out, float[9] K, float[2n], float[3n], float[4n] row-major 2x2
+ * sqrt-information factors with element [1] ignored, ceres.cpp:17-28).  This is the one entry point that owns memory: it
+ * packs the jobs into a cached pinned buffer (num_threads host threads), copies them to the current device, runs ONE
+ * lc_b200_lm_solve launch and copies states / radii / flags back before returning (synchronous, like the reference).
+ * ceres.cpp semantics kept: ptCnt < 3 -> rets = 1, result_trs = 1, state untouched (:84-91); rets / result_trs always
+ * written (:134-136); states written back only when valid (:137-144).  printSummary prints one line per job.
+ * The reference declares the function void; the int returned here (0 / cudaError_t / LC_E_*) can be ignored.
+ */
+int pnp_ceres_f32_omp(float** init_states, float** cam_Ks, float** pts2ds, float** pts3ds, float** icov_sqrtLs, int* ptCnts,
+                      int maxIterCnt, float function_tolerance, int printSummary, float* result_trs, int* rets, int job_count,
+                      int num_threads);
+/* single-problem form, ceres.cpp:72-83 */
+int pnp_ceres_f32(float* io_state_quat, const float* cam_K, const float* pts2d, const float* pts3d, const float* icov_sqrtL,
+                  int ptCnt, int maxIterCnt, float function_tolerance, int printSummary, float* result_tr, int* ret);
+/* frees the staging buffers cached by the two functions above */
+void lc_b200_compat_release(void);
 
 #ifdef __cplusplus
 }

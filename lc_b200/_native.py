@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("LC_B200_LIB") or os.path.join(_HERE, "liblc_b200.so")   # env override: instrumented builds (tools/)
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu", "lc_select.cu", "lc_eval.cu", "lc_init.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_dense.cu", "lc_select.cu", "lc_eval.cu", "lc_init.cu", "lc_compat.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "csrc", "lc_pose.cuh"),
            os.path.join(_HERE, "csrc", "lc_resident.cuh"),
            os.path.join(_ROOT, "include", "lc_b200.h")]
@@ -33,6 +33,8 @@ EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_cou
            "lc_b200_loss_fwd_bwd", "lc_b200_solve_loss", "lc_b200_pnp_jac_cov", "lc_b200_pnp_jac_cov_bwd",
            "lc_b200_dense_loss_fwd_bwd", "lc_b200_noc_bin_decode", "lc_b200_dense_select", "lc_b200_pose_errors",
            "lc_b200_select_pose", "lc_b200_pnp_init", "lc_b200_noc_bin_encode")
+# exports with their own signatures (not the (args*, stream) pattern)
+EXTRA_EXPORTS = ("lc_b200_last_kernels", "pnp_ceres_f32_omp", "pnp_ceres_f32", "lc_b200_compat_release")
 
 
 class NativeLibraryError(RuntimeError):
@@ -166,10 +168,11 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(lc_b200 has no CPU or PyTorch fallback)")
         handle = C.CDLL(LIB_PATH)
-        for name in EXPORTS:
+        for name in EXPORTS + EXTRA_EXPORTS:
             if not hasattr(handle, name):
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name}")
         handle.lc_b200_last_error.restype = C.c_char_p
+        handle.lc_b200_last_kernels.restype = C.c_char_p
         for name in EXPORTS[3:]:
             argt = {"lc_b200_dense_loss_fwd_bwd": lc_dense_args, "lc_b200_noc_bin_decode": lc_decode_args,
                     "lc_b200_dense_select": lc_select_args, "lc_b200_pose_errors": lc_eval_args,

@@ -4,7 +4,9 @@
 // batches with diagonal weights whose correspondences fit in one SM's shared memory; everything else (fp64
 // tensors, full 2x2 weights, tiny or huge N) goes to the streaming kernel (lc_stream.cu).  Both are hand-written
 // sm_100a kernels; there is no library or host fallback.
+#include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 #include "lc_pose.cuh"
 
@@ -12,6 +14,19 @@ namespace lc {
 
 static thread_local char g_err[256] = "";
 static thread_local int g_launches = 0;
+static thread_local char g_kernels[512] = "";
+
+void note_kernel(const char* fmt, ...) {
+    ++g_launches;
+    const size_t len = strlen(g_kernels);
+    if (len + 2 >= sizeof(g_kernels)) return;
+    if (len) { g_kernels[len] = '+'; g_kernels[len + 1] = 0; }
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_kernels + strlen(g_kernels), sizeof(g_kernels) - strlen(g_kernels), fmt, ap);
+    va_end(ap);
+}
+static void reset_notes() { g_launches = 0; g_kernels[0] = 0; }
 
 static int fail(int code, const char* msg) {
     snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -19,13 +34,12 @@ static int fail(int code, const char* msg) {
 }
 
 static int check_launch(int rc) {
-    g_launches = 1;
     if (rc != 0) return fail(rc, cudaGetErrorString(static_cast<cudaError_t>(rc)));
     return LC_OK;
 }
 
 static int dispatch_pose(const lc_args* a, int mode, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!a) return fail(LC_E_NULL, "args is NULL");
     if (a->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (a->B < 0 || a->N < 0) return fail(LC_E_BADARG, "B and N must be non-negative");
@@ -48,9 +62,7 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
         if (cap > 0) {
             int rc = check_launch(launch_resident_pose(*a, mode, st, cap));
             if (rc != LC_OK) return rc;
-            rc = check_launch(launch_stream_pose(*a, mode, st, cap));
-            if (rc == LC_OK) g_launches = 2;
-            return rc;
+            return check_launch(launch_stream_pose(*a, mode, st, cap));
         }
     }
     if (mode == (MODE_LM | MODE_LC) && a->N <= 64 && a->state.ptr) {
@@ -61,15 +73,13 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
         if (rc != LC_OK) return rc;
         lc_args a2 = *a;
         a2.pose = a->state;
-        rc = check_launch(launch_stream_pose(a2, MODE_LC, st));
-        if (rc == LC_OK) g_launches = 2;
-        return rc;
+        return check_launch(launch_stream_pose(a2, MODE_LC, st));
     }
     return check_launch(launch_stream_pose(*a, mode, st));
 }
 
 static int dispatch_jac(const lc_args* a, bool bwd, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!a) return fail(LC_E_NULL, "args is NULL");
     if (a->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (a->B < 0 || a->N < 0) return fail(LC_E_BADARG, "B and N must be non-negative");
@@ -81,7 +91,7 @@ static int dispatch_jac(const lc_args* a, bool bwd, void* stream) {
 }
 
 static int dispatch_dense(const lc_dense_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->sample <= 0 || d->top < 0 || d->left < 0 || d->top >= d->H || d->left >= d->W)
@@ -105,7 +115,7 @@ static int dispatch_dense(const lc_dense_args* d, void* stream) {
 }
 
 static int dispatch_decode(const lc_decode_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->H <= 0 || d->W <= 0) return fail(LC_E_BADARG, "bad B / H / W");
@@ -118,7 +128,7 @@ static int dispatch_decode(const lc_decode_args* d, void* stream) {
 }
 
 static int dispatch_encode(const lc_encode_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->H <= 0 || d->W <= 0) return fail(LC_E_BADARG, "bad B / H / W");
@@ -130,7 +140,7 @@ static int dispatch_encode(const lc_encode_args* d, void* stream) {
 }
 
 static int dispatch_select(const lc_select_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->H <= 0 || d->W <= 0 || d->sample <= 0) return fail(LC_E_BADARG, "bad B / H / W / sample");
@@ -151,7 +161,7 @@ static int dispatch_select(const lc_select_args* d, void* stream) {
 }
 
 static int dispatch_init(const lc_init_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->N < 0 || d->irls_rounds < 0 || d->irls_rounds > 16) return fail(LC_E_BADARG, "bad B / N / irls_rounds");
@@ -162,7 +172,7 @@ static int dispatch_init(const lc_init_args* d, void* stream) {
 }
 
 static int dispatch_eval(const lc_eval_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->M < 0) return fail(LC_E_BADARG, "B and M must be non-negative");
@@ -172,7 +182,7 @@ static int dispatch_eval(const lc_eval_args* d, void* stream) {
 }
 
 static int dispatch_candi(const lc_candi_args* d, void* stream) {
-    g_launches = 0;
+    reset_notes();
     if (!d) return fail(LC_E_NULL, "args is NULL");
     if (d->abi_version != LC_B200_ABI_VERSION) return fail(LC_E_BADARG, "abi_version mismatch");
     if (d->B < 0 || d->N <= 0 || d->Kc <= 0 || (d->mode != 0 && d->mode != 1)) return fail(LC_E_BADARG, "bad B / N / Kc / mode");
@@ -188,6 +198,7 @@ extern "C" {
 int lc_b200_abi_version(void) { return LC_B200_ABI_VERSION; }
 const char* lc_b200_last_error(void) { return lc::g_err; }
 int lc_b200_last_launch_count(void) { return lc::g_launches; }
+const char* lc_b200_last_kernels(void) { return lc::g_kernels; }
 
 int lc_b200_lm_solve(const lc_args* a, void* stream) { return lc::dispatch_pose(a, lc::MODE_LM, stream); }
 int lc_b200_loss_fwd_bwd(const lc_args* a, void* stream) { return lc::dispatch_pose(a, lc::MODE_LC, stream); }

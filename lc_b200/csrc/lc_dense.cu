@@ -13,6 +13,8 @@
 // bit logits with the MSB-error soft decoding of floatbits.py:99-160 (+ noc_scale and the model transform of
 // losses.py:16-45), step 4 routes d/d pts3d to the one bit channel per axis that carries a gradient.
 // lc_decode_kernel is the test-time decode (floatbits.py:33-47, 197-224).
+#include <atomic>
+
 #include "lc_resident.cuh"
 
 namespace lc {
@@ -404,6 +406,7 @@ int launch_encode(const lc_encode_args& d, cudaStream_t st) {
     const int64_t total = static_cast<int64_t>(d.B) * d.H * d.W;
     if (total == 0) return 0;
     lc_encode_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d);
+    note_kernel("lc::lc_encode_kernel");
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -417,21 +420,23 @@ int launch_decode(const lc_decode_args& d, cudaStream_t st) {
                      o.stride[0] % 4 == 0;
     if (vec) lc_decode_kernel_v4<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, st>>>(d);
     else lc_decode_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d);
+    note_kernel(vec ? "lc::lc_decode_kernel_v4" : "lc::lc_decode_kernel");
     return static_cast<int>(cudaGetLastError());
 }
 
 template <int NT, bool ZEBRA>
 static int launch_dense_t(const lc_dense_args& d, const lc_args& a, int n, int max_smem, cudaStream_t st) {
     const size_t smem = resident_smem_bytes(n);
-    static bool configured[64] = {};   // per device
+    static std::atomic<bool> configured[64];   // per instantiation and per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         const cudaError_t e = cudaFuncSetAttribute(lc_dense_kernel<NT, ZEBRA>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured[dev] = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     lc_dense_kernel<NT, ZEBRA><<<d.B, NT, smem, st>>>(d, a, round_up4(n));
+    note_kernel("lc::lc_dense_kernel<%d,%s>", NT, ZEBRA ? "zebra" : "xyz");
     return static_cast<int>(cudaGetLastError());
 }
 

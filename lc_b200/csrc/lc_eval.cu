@@ -185,11 +185,13 @@ __global__ void __launch_bounds__(kEvalNT) lc_select_pose_kernel(const lc_candi_
 
 int launch_pose_errors(const lc_eval_args& d, cudaStream_t st) {
     lc_pose_errors_kernel<<<d.B, kEvalNT, 0, st>>>(d);
+    note_kernel("lc::lc_pose_errors_kernel");
     return static_cast<int>(cudaGetLastError());
 }
 int launch_select_pose(const lc_candi_args& d, cudaStream_t st) {
     if (d.mode == 0) lc_select_pose_kernel<0><<<d.B, kEvalNT, 0, st>>>(d);
     else lc_select_pose_kernel<1><<<d.B, kEvalNT, 0, st>>>(d);
+    note_kernel("lc::lc_select_pose_kernel<%d>", d.mode);
     return static_cast<int>(cudaGetLastError());
 }
 

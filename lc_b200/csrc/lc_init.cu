@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(kInitNT) lc_init_kernel(const lc_init_args d) 
 
 int launch_init(const lc_init_args& d, cudaStream_t st) {
     lc_init_kernel<<<d.B, kInitNT, 0, st>>>(d);
+    note_kernel("lc::lc_init_kernel");
     return static_cast<int>(cudaGetLastError());
 }
 

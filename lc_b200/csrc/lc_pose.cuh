@@ -801,6 +801,10 @@ __device__ __forceinline__ void lc_six_warp(const lc_args& a, PoseShared& s, int
     LC_MARK(7);
 }
 
+// every launch site records the kernel it dispatched (lc_abi.cu): lc_b200_last_launch_count() / lc_b200_last_kernels() report
+// what actually ran, not what the caller expected
+void note_kernel(const char* fmt, ...);
+
 // host-side launch entry points implemented in lc_stream.cu / lc_resident.cu (return cudaError_t as int)
 int launch_stream_pose(const lc_args& a, int mode, cudaStream_t st, int n_skip_le = -1);
 int launch_stream_jac(const lc_args& a, bool bwd, cudaStream_t st);

@@ -19,6 +19,8 @@
 // per SM and one CTA's load / 6x6 sections overlap the other's point passes.
 //
 // Restrictions (anything else takes the streaming kernel): fp32 tensors, diagonal weights, 64 < N <= limit.
+#include <atomic>
+
 #include "lc_resident.cuh"
 
 namespace lc {
@@ -214,18 +216,18 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int g_max_smem = -1;
+// opt-in shared-memory limit of the CURRENT device, cached per device index (the ABI is re-entrant: relaxed atomics,
+// a race only repeats the query)
+static std::atomic<int> g_max_smem[64];
 
 static int max_optin_smem() {
-    if (g_max_smem < 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
-            cudaGetLastError();
-            v = 0;
-        }
-        g_max_smem = v;
-    }
-    return g_max_smem;
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const bool cached = dev >= 0 && dev < 64;
+    if (cached && (v = g_max_smem[dev].load(std::memory_order_relaxed)) > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cached) g_max_smem[dev].store(v, std::memory_order_relaxed);
+    return v;
 }
 
 bool resident_supported(const lc_args& a, int mode) {
@@ -265,15 +267,16 @@ template <int NT, int MODE, bool TM = false>
 static int launch_res_t(const lc_args& a, cudaStream_t st, int cap) {
     const int n_res = cap > 0 ? cap : a.N;   // points held on chip per pose
     const size_t smem = TM ? resident_smem_bytes_tm(n_res) : resident_smem_bytes(n_res);
-    static bool configured[64] = {};   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
+    static std::atomic<bool> configured[64];   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured[dev] = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     lc_resident_kernel<NT, MODE, TM><<<a.B, NT, smem, st>>>(a, round_up4(n_res), tma_mask_for(a), cap > 0 ? cap : 0x7fffffff);
+    note_kernel("lc::lc_resident_kernel<%d,%s,%s>", NT, MODE == MODE_LM ? "LM" : (MODE == MODE_LC ? "LC" : "LM|LC"), TM ? "TMEM" : "smem");
     return static_cast<int>(cudaGetLastError());
 }
 

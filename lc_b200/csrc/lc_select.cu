@@ -9,6 +9,8 @@
 //
 // The per-sample quantile is an exact order statistic: 4-pass 8-bit radix select over the fp32 bit patterns held in
 // shared memory (values are >= 0, so the bit patterns are ordered), followed by torch's fp32 lerp.
+#include <atomic>
+
 #include "lc_resident.cuh"
 
 namespace lc {
@@ -226,13 +228,14 @@ int launch_select(const lc_select_args& d, cudaStream_t st) {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return static_cast<int>(cudaGetLastError());
     if (smem + 4096 > static_cast<size_t>(max_smem)) return -1;
-    static bool configured[64] = {};
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
+    static std::atomic<bool> configured[64];
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
         const cudaError_t e = cudaFuncSetAttribute(lc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 4096);
         if (e != cudaSuccess) return static_cast<int>(e);
-        configured[dev] = true;
+        if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     lc_select_kernel<<<d.B, kSelNT, smem, st>>>(d);
+    note_kernel("lc::lc_select_kernel");
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -610,6 +610,8 @@ static int launch_pose_t(const lc_args& a, cudaStream_t st, int skip) {
         case 128: lc_pose_kernel<T, 128, MODE><<<a.B, 128, 0, st>>>(a, skip); break;
         default: lc_pose_kernel<T, 256, MODE><<<a.B, 256, 0, st>>>(a, skip); break;
     }
+    note_kernel("lc::lc_pose_kernel<%s,%d,%s>", sizeof(T) == 4 ? "float" : "double", stream_threads_for(a.N),
+                MODE == MODE_LM ? "LM" : (MODE == MODE_LC ? "LC" : "LM|LC"));
     return static_cast<int>(cudaGetLastError());
 }
 
@@ -635,6 +637,7 @@ static int launch_jac_t(const lc_args& a, cudaStream_t st) {
         default: LC_JAC_LAUNCH(256); break;
     }
 #undef LC_JAC_LAUNCH
+    note_kernel("lc::%s<%s,%d>", BWD ? "lc_jac_bwd_kernel" : "lc_jac_kernel", sizeof(T) == 4 ? "float" : "double", stream_threads_for(a.N));
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -17,7 +17,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liblc_oracle.so")
 _lib = None
 
+# rule switches of oracle/lm_oracle.c (every from-memory Ceres rule is switchable; tools/lm_sensitivity.py flips them)
 LM_TOL_NEEDS_SUCCESS = 1
+LM_INVALID_DIV_DEC, LM_GRAD_TEST_ALWAYS, LM_REPORT_CURRENT_RADIUS, LM_SOLVE_NORMAL_EQ = 2, 4, 8, 16
+LM_TOL_KEEP_CANDIDATE, LM_GRAD_NORM_PLAIN, LM_SCALE_NO_PLUS_ONE = 32, 64, 128
 LM_TRACE_COLS = 4
 TERM_NAMES = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}
 

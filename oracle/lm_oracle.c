@@ -45,10 +45,33 @@
 #include <omp.h>
 #endif
 
-/* Ceres >= 2.1 only declares parameter/function-tolerance convergence after at least one
- * successful step ("atleast_one_successful_step"); earlier releases test unconditionally.
- * Recollection, not verifiable offline -> kept switchable.  Default (flags = 1) = guarded. */
+/* Every rule of the trust-region loop that is restated from memory (not from ceres.cpp, not from the documented
+ * Solver::Options defaults) is switchable, so that tools/lm_sensitivity.py can measure how much the returned pose
+ * depends on it (profiles/lm_unpinned_sensitivity.md).  flags = LM_TOL_NEEDS_SUCCESS (1) is the working definition.
+ *
+ *   LM_TOL_NEEDS_SUCCESS      parameter/function-tolerance convergence only after at least one successful step
+ *                             ("atleast_one_successful_step"); off = tested unconditionally
+ *   LM_INVALID_DIV_DEC        invalid step (model_cost_change <= 0 / non-finite solve): radius /= dec, dec *= 2 like a
+ *                             rejected step; default = LevenbergMarquardtStrategy::StepIsInvalid, radius *= 0.5
+ *   LM_GRAD_TEST_ALWAYS       gradient-tolerance test after every finalised iteration; default = only after a
+ *                             successful step
+ *   LM_REPORT_CURRENT_RADIUS  reported trust-region radius = the strategy's radius at termination; default = the radius
+ *                             recorded in the last finalised IterationSummary (iterations.back())
+ *   LM_SOLVE_NORMAL_EQ        step from a Cholesky factorisation of J^T J + D^2 (what the CUDA kernel does); default =
+ *                             Householder QR of [J; D] (DENSE_QR)
+ *   LM_TOL_KEEP_CANDIDATE     a candidate that triggers the parameter/function tolerance is kept when it lowers the cost;
+ *                             default = discarded (Minimize() returns before HandleSuccessfulStep)
+ *   LM_GRAD_NORM_PLAIN        gradient max-norm = |g|_inf; default = |x - Plus(x, -g)|_inf evaluated in floating point
+ *   LM_SCALE_NO_PLUS_ONE      Jacobi scaling 1/||J_col||; default = 1/(1 + ||J_col||)
+ */
 #define LM_TOL_NEEDS_SUCCESS 1
+#define LM_INVALID_DIV_DEC 2
+#define LM_GRAD_TEST_ALWAYS 4
+#define LM_REPORT_CURRENT_RADIUS 8
+#define LM_SOLVE_NORMAL_EQ 16
+#define LM_TOL_KEEP_CANDIDATE 32
+#define LM_GRAD_NORM_PLAIN 64
+#define LM_SCALE_NO_PLUS_ONE 128
 
 /* ---------------- Jet<double,6> ---------------- */
 typedef struct { double v; double d[6]; } jet;
@@ -196,6 +219,34 @@ static int qr_solve6(double* A, double* b, int m, double y[6]) {
     return 1;
 }
 
+/* LM_SOLVE_NORMAL_EQ: (J^T J + diag(d2)) y = J^T r by a 6x6 Cholesky factorisation.  Returns 0 on breakdown. */
+static int chol_solve6(const double* J, const double* r, int m, const double d2[6], double y[6]) {
+    double A[36], g[6], L[36];
+    memset(A, 0, sizeof(A)); memset(g, 0, sizeof(g)); memset(L, 0, sizeof(L));
+    for (int i = 0; i < m; ++i)
+        for (int a = 0; a < 6; ++a) {
+            g[a] += J[(size_t)i * 6 + a] * r[i];
+            for (int b = a; b < 6; ++b) A[a * 6 + b] += J[(size_t)i * 6 + a] * J[(size_t)i * 6 + b];
+        }
+    for (int a = 0; a < 6; ++a) { A[a * 6 + a] += d2[a]; for (int b = 0; b < a; ++b) A[a * 6 + b] = A[b * 6 + a]; }
+    for (int j = 0; j < 6; ++j) {
+        double d = A[j * 6 + j];
+        for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > 0.0) || !isfinite(d)) return 0;
+        L[j * 6 + j] = sqrt(d);
+        for (int i = j + 1; i < 6; ++i) {
+            double v = A[i * 6 + j];
+            for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = v / L[j * 6 + j];
+        }
+    }
+    double z[6];
+    for (int i = 0; i < 6; ++i) { double v = g[i]; for (int k = 0; k < i; ++k) v -= L[i * 6 + k] * z[k]; z[i] = v / L[i * 6 + i]; }
+    for (int i = 5; i >= 0; --i) { double v = z[i]; for (int k = i + 1; k < 6; ++k) v -= L[k * 6 + i] * y[k]; y[i] = v / L[i * 6 + i]; }
+    for (int k = 0; k < 6; ++k) if (!isfinite(y[k])) return 0;
+    return 1;
+}
+
 /* ceres/rotation.h */
 static void quat_to_aa(const double q[4], double aa[3]) {
     const double s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
@@ -219,6 +270,17 @@ static void aa_to_quat(const double aa[3], double q[4]) {
 }
 
 enum { TERM_CONVERGENCE = 0, TERM_NO_CONVERGENCE = 1, TERM_FAILURE = 2 };
+
+static double grad_max_norm(const double x[6], const double g[6], int flags) {
+    double gmax = 0;
+    for (int k = 0; k < 6; ++k) {
+        double d;
+        if (flags & LM_GRAD_NORM_PLAIN) d = fabs(g[k]);
+        else { const volatile double xs = x[k] + (-g[k]); d = fabs(x[k] - xs); }
+        if (d > gmax) gmax = d;
+    }
+    return gmax;
+}
 
 /* Trace row per finalised iteration: [cost, radius, step_successful, gradient_max_norm] */
 #define LM_TRACE_COLS 4
@@ -275,11 +337,10 @@ void lm_oracle_pose(float* io_state7, const float* K9, const float* pts2d, const
     for (int k = 0; k < 6; ++k) {
         double s = 0;
         for (int i = 0; i < m; ++i) s += J[(size_t)i * 6 + k] * J[(size_t)i * 6 + k];
-        scale[k] = 1.0 / (1.0 + sqrt(s));
+        scale[k] = 1.0 / (((flags & LM_SCALE_NO_PLUS_ONE) ? 0.0 : 1.0) + sqrt(s));
     }
     for (int i = 0; i < m; ++i) for (int k = 0; k < 6; ++k) J[(size_t)i * 6 + k] *= scale[k];
-    gmax = 0;
-    for (int k = 0; k < 6; ++k) { const volatile double xs = x[k] + (-g[k]); const double d = fabs(x[k] - xs); if (d > gmax) gmax = d; }
+    gmax = grad_max_norm(x, g, flags);
     xnorm = 0; for (int k = 0; k < 6; ++k) xnorm += x[k] * x[k]; xnorm = sqrt(xnorm);
     step_ok = 1;
 
@@ -289,7 +350,7 @@ void lm_oracle_pose(float* io_state7, const float* K9, const float* pts2d, const
         if (step_ok) memcpy(best, x, sizeof(best));
         if (trace) { double* tr = trace + (size_t)it * LM_TRACE_COLS; tr[0] = cost; tr[1] = radius; tr[2] = step_ok; tr[3] = gmax; }
         if (it >= max_iter) { term = TERM_NO_CONVERGENCE; break; }
-        if (step_ok && gmax <= gtol) { term = TERM_CONVERGENCE; break; }
+        if ((step_ok || (flags & LM_GRAD_TEST_ALWAYS)) && gmax <= gtol) { term = TERM_CONVERGENCE; break; }
         if (radius <= min_radius) { term = TERM_CONVERGENCE; break; }
         ++it;
 
@@ -301,13 +362,20 @@ void lm_oracle_pose(float* io_state7, const float* K9, const float* pts2d, const
                 diag[k] = fmin(fmax(s, min_diag), max_diag);
             }
         }
-        memcpy(lhs, J, sizeof(double) * (size_t)m * 6);
-        memset(lhs + (size_t)m * 6, 0, sizeof(double) * 36);
-        for (int k = 0; k < 6; ++k) lhs[(size_t)(m + k) * 6 + k] = sqrt(diag[k] / radius);
-        memcpy(rhs, r, sizeof(double) * m);
-        memset(rhs + m, 0, sizeof(double) * 6);
         double step[6];
-        int valid = qr_solve6(lhs, rhs, m + 6, step);
+        int valid;
+        if (flags & LM_SOLVE_NORMAL_EQ) {
+            double d2[6];
+            for (int k = 0; k < 6; ++k) d2[k] = diag[k] / radius;
+            valid = chol_solve6(J, r, m, d2, step);
+        } else {
+            memcpy(lhs, J, sizeof(double) * (size_t)m * 6);
+            memset(lhs + (size_t)m * 6, 0, sizeof(double) * 36);
+            for (int k = 0; k < 6; ++k) lhs[(size_t)(m + k) * 6 + k] = sqrt(diag[k] / radius);
+            memcpy(rhs, r, sizeof(double) * m);
+            memset(rhs + m, 0, sizeof(double) * 6);
+            valid = qr_solve6(lhs, rhs, m + 6, step);
+        }
         reuse_diag = 1;
         double model_change = 0;
         if (valid) {
@@ -321,7 +389,9 @@ void lm_oracle_pose(float* io_state7, const float* K9, const float* pts2d, const
         }
         if (!valid) {
             if (++n_invalid >= 5) { term = TERM_FAILURE; have_iter = 1; break; }
-            radius *= 0.5; reuse_diag = 1;                   /* StepIsInvalid */
+            if (flags & LM_INVALID_DIV_DEC) { radius = radius / dec; dec *= 2.0; }
+            else radius *= 0.5;                              /* StepIsInvalid */
+            reuse_diag = 1;
             step_ok = 0;
             continue;
         }
@@ -333,9 +403,11 @@ void lm_oracle_pose(float* io_state7, const float* K9, const float* pts2d, const
         const int tol_armed = !(flags & LM_TOL_NEEDS_SUCCESS) || any_success;
         /* ParameterToleranceReached */
         double sn = 0; for (int k = 0; k < 6; ++k) sn += (x[k] - xc[k]) * (x[k] - xc[k]); sn = sqrt(sn);
-        if (tol_armed && sn <= ptol * (xnorm + ptol)) { term = TERM_CONVERGENCE; break; }
-        /* FunctionToleranceReached */
-        if (tol_armed && fabs(cost - cost_c) <= ftol * cost) { term = TERM_CONVERGENCE; break; }
+        if (tol_armed && (sn <= ptol * (xnorm + ptol) || fabs(cost - cost_c) <= ftol * cost)) {   /* parameter, then function tolerance */
+            if ((flags & LM_TOL_KEEP_CANDIDATE) && cost_c < cost) memcpy(best, xc, sizeof(best));
+            term = TERM_CONVERGENCE;
+            break;
+        }
 
         const double rho = cost_c >= DBL_MAX ? -DBL_MAX : (cost - cost_c) / model_change;
         if (rho > min_rel_dec) {
@@ -343,8 +415,7 @@ void lm_oracle_pose(float* io_state7, const float* K9, const float* pts2d, const
             xnorm = 0; for (int k = 0; k < 6; ++k) xnorm += x[k] * x[k]; xnorm = sqrt(xnorm);
             if (!evaluate(&P, x, &cost, r, J, g)) { term = TERM_FAILURE; break; }
             for (int i = 0; i < m; ++i) for (int k = 0; k < 6; ++k) J[(size_t)i * 6 + k] *= scale[k];
-            gmax = 0;
-            for (int k = 0; k < 6; ++k) { const volatile double xs = x[k] + (-g[k]); const double d = fabs(x[k] - xs); if (d > gmax) gmax = d; }
+            gmax = grad_max_norm(x, g, flags);
             radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3));
             radius = fmin(max_radius, radius);
             dec = 2.0; reuse_diag = 0; step_ok = 1; any_success = 1;
@@ -357,7 +428,7 @@ done:
     if (out_iters) *out_iters = it;
     if (out_term) *out_term = term;
     if (out_x6) memcpy(out_x6, best, sizeof(best));
-    *out_radius = (float)reported_radius;
+    *out_radius = (float)((flags & LM_REPORT_CURRENT_RADIUS) ? radius : reported_radius);
     *out_invalid = (term != TERM_CONVERGENCE);
     if (term == TERM_CONVERGENCE) {
         double q[4];

@@ -254,3 +254,23 @@ def test_selection_oracle_properties(oracle):
         assert (np.abs(q["valid"].sum(1) - 0.8 * N) <= 2).all()
         assert not (qm["valid"] & ~m["valid"]).any()
         assert (np.abs(qm["valid"].sum(1) - 0.8 * m["valid"].sum(1)) <= 2).all()
+
+
+def test_lm_oracle_rule_switches_are_wired(oracle):
+    """The from-memory Ceres rules are flags of the oracle (tools/lm_sensitivity.py, profiles/lm_unpinned_sensitivity.md):
+    the guard rule decides whether a restart from a converged pose takes 1 or 2 iterations, keeping the tolerance-triggering
+    candidate moves the pose by the early-stop gap, QR vs normal equations agree to 1e-10 on well-posed problems."""
+    c = make_correspondences(24, 64, 77).to(torch.float32)
+    L = torch.diag_embed((c.inv_std ** 2).sqrt())
+    base = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, c.start)
+    ne = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, c.start, flags=oracle.LM_TOL_NEEDS_SUCCESS | oracle.LM_SOLVE_NORMAL_EQ)
+    assert np.array_equal(base["iters"], ne["iters"]) and np.abs(base["x6"] - ne["x6"]).max() < 1e-10
+    keep = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, c.start, flags=oracle.LM_TOL_NEEDS_SUCCESS | oracle.LM_TOL_KEEP_CANDIDATE)
+    assert np.array_equal(base["iters"], keep["iters"])
+    d = np.abs(base["x6"][:, :3] - keep["x6"][:, :3]).max(axis=1)
+    assert (d > 0).all() and d.max() < 5e-3
+    again = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, base["states"])
+    unguarded = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, base["states"], flags=0)
+    assert (again["iters"] == 2).all() and (unguarded["iters"] == 1).all()
+    # candidate discarded: the start comes back (through quaternion -> angle-axis -> quaternion in fp32)
+    assert np.allclose(unguarded["states"], base["states"], rtol=3e-7, atol=1e-7)
