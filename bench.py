@@ -12,9 +12,13 @@ Workload at every N: B=1024 poses x N=4096 correspondences PER GPU (weak scaling
 pose with no data-path collective, the only exchange is the 16-byte all-reduce of the mean loss).
 
 `value`    poses/s with inputs resident in HBM (CUDA events, max over ranks).
-`e2e`      the same metric through the public API with HOST (pinned) input buffers: per step the H2D copy
-           of K/start/pts3d/pts2d/inv_std/bbox and the D2H read of loss + solved states are inside the
-           timed region (copies overlap the previous step's kernel on a second stream).
+`e2e`      the same metric through the public API with HOST (pinned) buffers on both sides: per step the H2D copy
+           of K/start/pts3d/pts2d/inv_std/bbox and the D2H read of the WHOLE result (loss, solved states and the
+           gradients d/d pts3d, d/d inv_std) are inside the timed region; uploads, the kernel and downloads run on three
+           streams and overlap across steps.  Pinned buffers are allocated after binding the rank to the CPUs NVML
+           reports as local to its GPU (NUMA-local first touch).  `e2e.grads_on_device` is the variant that leaves the
+           gradients on the device (what a training pipeline does).
+`gpu_launches` / `roofline.kernel` are OBSERVED: the library reports the kernels each call dispatched.
 `roofline` HBM: algorithmic bytes per launch (48*N + 228 per pose) / launch time, against the
            measured copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the CPU oracle (C/OpenMP port of the reference path; the reference's
@@ -52,6 +56,8 @@ def parse():
     ap.add_argument("--pipeline", default="p3", choices=["p3", "p1", "p2"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--points", type=int, default=N_PTS)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch poses PER GPU (default); strong: --batch poses in total, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -178,6 +184,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers are allocated, so their
+    pages are first-touched on the GPU's NUMA node and the H2D/D2H DMA does not cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            idx = int(vis.split(",")[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "NVML reported no local CPUs inside this process's affinity mask; not bound"
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to {len(cpus)} CPUs local to GPU {idx} (NVML cpu affinity) before allocating pinned buffers"
+    except Exception as e:  # pragma: no cover - depends on the box
+        return f"not bound ({type(e).__name__}: {e})"
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -188,15 +217,19 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(pipeline: str):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(pipeline: str, kernel: str):
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/traffic.json), reported only when that capture was taken on the kernel this run
+    dispatched; otherwise null (the capture predates the current kernels)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(pipeline)
-        except Exception:
-            return None
-    return None
+    try:
+        t = json.load(open(p))
+        e = t.get(pipeline)
+        if isinstance(e, dict) and e.get("kernel") and e["kernel"] in kernel:
+            return e.get("bytes"), f"profiles/traffic.json: ncu capture {e.get('capture')} at commit {e.get('commit')}"
+    except Exception:
+        pass
+    return None, "no ncu capture of the dispatched kernel committed"
 
 
 def main():
@@ -204,10 +237,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"isolated LC op {a.pipeline}: B={a.batch}/GPU x N={a.points} dense correspondences (BASELINE.json configs[1])"
+    if a.scaling == "strong":
+        if a.batch % world:
+            raise SystemExit("--scaling strong needs --batch divisible by the number of ranks")
+        a.batch //= world
+    per = "/GPU" if a.scaling == "weak" else f" in total ({a.batch}/GPU)"
+    workload = f"isolated LC op {a.pipeline}: B={a.batch * (world if a.scaling == 'strong' else 1)}{per} x N={a.points} dense correspondences (BASELINE.json configs[1])"
+    rot_mb = a.batch * a.points * 28 / 1e6
     config = {"workload": workload, "pipeline": a.pipeline, "batch_per_gpu": a.batch, "points": a.points,
               "parallelism": f"batch-sharded x{world}",
-              "l2": f"inputs rotate over {N_ROTATE} distinct resident batches ({N_ROTATE}x{a.batch * a.points * 28 / 1e6:.0f} MB) > 126 MB L2"}
+              "l2": f"inputs rotate over {N_ROTATE} distinct resident batches ({N_ROTATE}x{rot_mb:.0f} MB) > 126 MB L2"}
 
     if a.impl == "reference":
         # The reference's own CPU implementation of the path: its Ceres extension cannot be built in this image, so
@@ -216,8 +255,11 @@ def main():
             return
         sample = cpu_sample_size(a.batch)
         v, dt, cores = run_cpu_port(a.pipeline, a.points, sample, max(1, a.steps), max(0, a.warmup))
+        config["reference_arm_sample"] = (f"each step of this arm solves {sample} poses (not {a.batch}): OpenMP over independent poses on {cores} "
+                                          "host cores, throughput is per pose")
+        config["poses_per_step"] = sample
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "poses/s", "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(0, a.warmup), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": a.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "gpu_launches": 0,
                 "cpu_baseline": {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
                                  "sample": f"{sample} poses x N={a.points} per step, {a.steps} steps, OpenMP over poses"},
@@ -243,13 +285,19 @@ def main():
     nat.lib()
 
     B, N = a.batch, a.points
-    # synthetic inputs: distinct seeds per rank and per rotating slot; planar layout as the dense call site gives
+    numa_note = bind_to_gpu_numa_node(local_rank)
+    # synthetic inputs: distinct seeds per rank and per rotating slot; planar layout as the dense call site gives.
+    # The rotating set is larger than the 126 MB L2 (more slots when the per-GPU batch is small).
+    n_rot = N_ROTATE if N_ROTATE * rot_mb > 2 * 126 else min(64, int(2 * 126 / rot_mb) + 1)
+    if n_rot != N_ROTATE:
+        config["l2"] = f"inputs rotate over {n_rot} distinct resident batches ({n_rot}x{rot_mb:.0f} MB) > 126 MB L2"
     host, devb = [], []
-    for slot in range(N_ROTATE):
+    for slot in range(n_rot):
         c = make_correspondences(B, N, 10 + slot + 100 * rank).to(torch.float32)
         h = dict(K=c.K, start=c.start, pose=c.pose, pts3d=c.pts3d.transpose(1, 2).contiguous(),
                  pts2d=c.pts2d.transpose(1, 2).contiguous(), inv_std=c.inv_std.transpose(1, 2).contiguous(), bbox=c.bbox_3d)
-        host.append({k: v.pin_memory() for k, v in h.items()})
+        if slot < N_ROTATE:
+            host.append({k: v.pin_memory() for k, v in h.items()})
         devb.append({k: v.to(dev) for k, v in h.items()})
     go = torch.full((B,), 1.0 / (B * world), dtype=torch.float32, device=dev)   # d mean / d loss_b
 
@@ -266,6 +314,8 @@ def main():
     ev_kernel = [torch.cuda.Event() for _ in range(RING)]
     ev_reduced = [torch.cuda.Event() for _ in range(RING)]
     counter = [0]
+    handle = nat.lib()
+    observed = {"launches": 0, "kernels": set()}
 
     def step(d, out):
         p3, p2, s = views(d)
@@ -284,6 +334,9 @@ def main():
             r = loss_fwd_bwd(d["K"], d["pose"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, loss_sum=acc)
         else:
             r = lm_solve(d["K"], p3, p2, s, d["start"], weight_mode=nat.W_INV_STD)
+        # what the library actually dispatched for this call (lc_abi.cu: every launch site records itself)
+        observed["launches"] += handle.lc_b200_last_launch_count()
+        observed["kernels"].add(handle.lc_b200_last_kernels().decode())
         m = None
         if acc is not None:
             # the path's only exchange: one 16-byte all-reduce of [sum of losses, count] (losses.py:334,386 take the mean)
@@ -303,19 +356,22 @@ def main():
     if a.pipeline == "p3":
         r0, _ = step(devb[0], None)
         outs = {k: r0[k] for k in ("states", "radius", "invalid", "iters", "loss", "flags", "g_pts3d", "g_inv_std")}
-    for i in range(max(3, a.warmup)):
-        step(devb[i % N_ROTATE], outs)
+    warm = max(3, a.warmup)
+    for i in range(warm):
+        step(devb[i % n_rot], outs)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    observed["launches"] = 0
     e0.record()
     for i in range(a.steps):
-        step(devb[i % N_ROTATE], outs)
+        step(devb[i % n_rot], outs)
     e1.record()
     barrier()
+    launches_timed = observed["launches"]
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -324,56 +380,81 @@ def main():
     ms = float(t.item())
     value = world * B * a.steps / (ms * 1e-3)
 
-    # ---- end to end: host buffers in, loss + states out, copies overlapped with compute on a second stream ----
+    # ---- end to end: host buffers in, the whole result out (loss, states, gradients), three streams ----
     e2e = None
     if not a.no_e2e:
-        copy_stream = torch.cuda.Stream(dev)
+        up_stream, down_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         comp = torch.cuda.current_stream(dev)
         stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
-        h_loss = torch.empty(B, dtype=torch.float32).pin_memory()
-        h_state = torch.empty(B, 7, dtype=torch.float32).pin_memory()
         keys = ("K", "start", "pts3d", "pts2d", "inv_std", "bbox") if a.pipeline != "p1" else ("K", "pose", "pts3d", "pts2d", "inv_std", "bbox")
         h2d = sum(host[0][k].numel() * 4 for k in keys)
-        d2h = h_loss.numel() * 4 + (h_state.numel() * 4 if a.pipeline != "p1" else 0)
+        small = ("loss", "states") if a.pipeline == "p3" else (("loss",) if a.pipeline == "p1" else ("radius", "states"))
+        big = ("g_pts3d", "g_inv_std") if a.pipeline != "p2" else ()
 
         def upload(i):
             sl = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[sl])
+            with torch.cuda.stream(up_stream):
+                up_stream.wait_event(freed[sl])
                 for k in keys:
-                    stage[sl][k].copy_(host[i % N_ROTATE][k], non_blocking=True)
-                ready[sl].record(copy_stream)
+                    stage[sl][k].copy_(host[i % len(host)][k], non_blocking=True)
+                ready[sl].record(up_stream)
 
-        def e2e_loop(n):
+        def e2e_loop(n, with_grads):
+            # result slots: the kernel of step i writes outs2[i % 2]; its download runs on down_stream while step i+1 computes
+            res_keys = small + (big if with_grads else ())
+            done = [torch.cuda.Event() for _ in range(2)]
+            taken = [torch.cuda.Event() for _ in range(2)]
             for sl in range(2):
                 freed[sl].record(comp)
+                taken[sl].record(down_stream)
             upload(0)
             for i in range(n):
+                sl = i % 2
                 if i + 1 < n:
                     upload(i + 1)
-                comp.wait_event(ready[i % 2])
-                r, _ = step(stage[i % 2], outs)
-                freed[i % 2].record(comp)
-                h_loss.copy_(r["loss"] if a.pipeline != "p2" else r["radius"], non_blocking=True)
-                if a.pipeline != "p1":
-                    h_state.copy_(r["states"], non_blocking=True)
+                comp.wait_event(ready[sl])
+                comp.wait_event(taken[sl])            # the previous download of this result slot has finished
+                r, _ = step(stage[sl], outs2[sl] if a.pipeline == "p3" else None)
+                freed[sl].record(comp)
+                done[sl].record(comp)
+                with torch.cuda.stream(down_stream):
+                    down_stream.wait_event(done[sl])
+                    for k in res_keys:
+                        h_out[sl][k].copy_(r[k], non_blocking=True)
+                        r[k].record_stream(down_stream)
+                    taken[sl].record(down_stream)
+            down_stream.synchronize()
             comp.synchronize()
 
-        n_e2e = max(5, min(a.steps, 20))
-        e2e_loop(3)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_loop(n_e2e)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * n_e2e / float(tt.item()), "unit": "poses/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": n_e2e,
-               "note": "pinned host inputs -> H2D -> one kernel -> D2H of loss+states; gradients stay on the device (they feed the network backward there)"}
+        r_probe, _ = step(devb[0], None)
+        outs2 = [outs, {k: torch.empty_like(v) for k, v in outs.items()}] if a.pipeline == "p3" else [None, None]
+        h_out = [{k: torch.empty(r_probe[k].shape, dtype=r_probe[k].dtype).pin_memory() for k in small + big} for _ in range(2)]
+        d2h_small = sum(h_out[0][k].numel() * h_out[0][k].element_size() for k in small)
+        d2h_big = sum(h_out[0][k].numel() * h_out[0][k].element_size() for k in big)
+
+        def timed(with_grads):
+            n_e2e = max(5, min(a.steps, 20))
+            e2e_loop(3, with_grads)
+            barrier()
+            t0 = time.perf_counter()
+            e2e_loop(n_e2e, with_grads)
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return world * B * n_e2e / float(tt.item()), n_e2e, float(tt.item()) / n_e2e
+
+        v_full, n_e2e, s_full = timed(True)
+        v_dev, _, s_dev = timed(False)
+        e2e = {"value": v_full, "unit": "poses/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_small + d2h_big, "steps": n_e2e,
+               "h2d_gbs_per_gpu": h2d / s_full / 1e9, "d2h_gbs_per_gpu": (d2h_small + d2h_big) / s_full / 1e9,
+               "numa": numa_note,
+               "note": "pinned host inputs -> H2D -> one kernel -> D2H of loss, states AND gradients; three streams, copies overlap the neighbouring steps' kernels",
+               "grads_on_device": {"value": v_dev, "unit": "poses/s", "d2h_bytes_per_step": d2h_small, "h2d_gbs_per_gpu": h2d / s_dev / 1e9,
+                                   "note": "same loop, gradients stay on the device (they feed the network backward there)"}}
 
     if rank != 0:
         if world > 1:
@@ -384,11 +465,12 @@ def main():
     bytes_per_launch = B * algorithmic_bytes_per_pose(a.pipeline, N)
     launch_s = ms * 1e-3 / a.steps
     achieved = bytes_per_launch / launch_s / 1e9
-    kernel = {"p3": "lc::lc_resident_kernel<256, LM|LC>", "p1": "lc::lc_resident_kernel<128, LC, TMEM> (model points in tensor memory, 4 CTAs/SM)", "p2": "lc::lc_resident_kernel<192, LM>"}[a.pipeline]
+    kernel = " | ".join(sorted(observed["kernels"]))
+    traffic, traffic_src = ncu_traffic(a.pipeline, kernel)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(a.pipeline), "kernel": kernel, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "launch_us": launch_s * 1e6,
-                "note": "arithmetic/latency bound, not HBM bound (DESIGN.md 4.9): ~1.5k instructions per point incl. an fp64 LM; frac is against the measured HBM copy peak as BASELINE.json asks"}
+                "note": "arithmetic/latency bound, not HBM bound (DESIGN.md 4.9): an fp64 LM plus ~0.5 kFMA per point; frac is against the measured HBM copy peak as BASELINE.json asks"}
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
@@ -397,9 +479,9 @@ def main():
         cpu = {"value": v, "unit": "poses/s", "cores": cores, "kind": "port",
                "sample": f"{sample} poses x N={N}, 3 timed passes after 1 warm-up, OpenMP over poses ({dt * 1e3:.0f} ms/pass)"}
 
-    line = {"metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps,
+    line = {"metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -66,6 +66,8 @@ class _LossCovMixed(torch.autograd.Function):
         need = tuple(ctx.needs_input_grad[:3])
         out = loss_fwd_bwd(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, max_err_len=max_err_len,
                            rel_thresh=rel_thresh, w_e_thresh=w_e_thresh, need=need)
+        # the fused launch already produced d loss_b / d input; they live as long as the graph does (backward may run more
+        # than once under retain_graph=True, like the reference's autograd graph)
         ctx.grads = (out["g_pts3d"], out["g_pts2d"], out["g_inv_std"])
         ctx.shapes = (pts3d.shape, pts2d.shape, inv_std.shape)
         return out["loss"]
@@ -82,7 +84,6 @@ class _LossCovMixed(torch.autograd.Function):
             g = g * go
             # inputs that were broadcast over the batch (e.g. the shared pixel grid) get the summed gradient
             res.append(g if g.shape == shp else g.sum_to_size(shp))
-        ctx.grads = None
         return (*res, None, None, None, None, None, None, None)
 
 

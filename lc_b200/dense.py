@@ -99,8 +99,7 @@ class _DensePoseLoss(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss):
-        gx, gl, gs = ctx.grads
-        ctx.grads = None
+        gx, gl, gs = ctx.grads   # kept for the lifetime of the graph: backward may run again under retain_graph=True
         need = ctx.needs_input_grad
         go4 = grad_loss.reshape(-1, 1, 1, 1)
         return (gx * go4 if need[0] else None, gl * go4 if need[1] else None,
@@ -135,7 +134,6 @@ class _DensePoseLossNocBin(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss):
         gb, gl, gs = ctx.grads
-        ctx.grads = None
         need = ctx.needs_input_grad
         go4 = grad_loss.reshape(-1, 1, 1, 1)
         return (gb * go4 if need[0] else None, gl * go4 if need[1] else None,

@@ -66,9 +66,7 @@ class _PnPJacCov(torch.autograd.Function):
         return gw.sum_to_size(weights.shape) if gw.shape != weights.shape else gw, None, None, None, None
 
 
-def weighted_pnp_jac_wrt_pts2d(pts2d: Tensor, state_gt: Tensor, cam_K: Tensor, pts3d: Tensor, weights: Tensor,
-                               with_cov: bool = False):
-    """Reference signature (``pnp_auto.py:111``)."""
+def _flatten_inputs(pts2d, state_gt, cam_K, pts3d, weights):
     batched = pts3d.dim() != 2
     p3 = pts3d.detach() if batched else pts3d.detach().unsqueeze(0)
     p3 = p3.reshape((-1,) + tuple(p3.shape[-2:]))
@@ -78,25 +76,47 @@ def weighted_pnp_jac_wrt_pts2d(pts2d: Tensor, state_gt: Tensor, cam_K: Tensor, p
     w = _weights_as_bn2(w.reshape((B,) + tuple(w.shape[len(lead) if batched else 1:])), B, N)
     pose = state_gt.detach().reshape(-1, 7).expand(B, 7)
     K = cam_K.detach().reshape(-1, 3, 3).expand(B, 3, 3)
-    p2 = (pts2d.detach() if batched else pts2d.detach().unsqueeze(0)).expand(tuple(lead) + (N, 2) if batched else (1, N, 2)).reshape(B, N, 2)
-    jac, cov, _ = _PnPJacCov.apply(w, pose, K, p3, p2)
+    p2 = (pts2d if batched else pts2d.unsqueeze(0)).expand(tuple(lead) + (N, 2) if batched else (1, N, 2)).reshape(B, N, 2)
+    return w, pose, K, p3, p2, lead, N
+
+
+def weighted_pnp_jac_wrt_pts2d(pts2d: Tensor, state_gt: Tensor, cam_K: Tensor, pts3d: Tensor, weights: Tensor,
+                               with_cov: bool = False):
+    """Reference signature (``pnp_auto.py:111``)."""
+    w, pose, K, p3, p2, lead, N = _flatten_inputs(pts2d, state_gt, cam_K, pts3d, weights)
+    jac, cov, _ = _PnPJacCov.apply(w, pose, K, p3, p2.detach())
     jac = jac.reshape(lead + (6, N, 2))
     cov = cov.reshape(lead + (6, 6))
     return (jac, cov) if with_cov else jac
 
 
+class _RightUpdate(torch.autograd.Function):
+    """``nll_update`` of the reference (``pnp_utils.py:118-131``): zero in value, its vector-Jacobian product w.r.t. the
+    measured points is ``g^T d(update)/d(pts2d) = g^T jac``.  The backward is written with differentiable torch ops on
+    ``jac``, so ``autograd.grad(update, pts2d, create_graph=True)`` can be differentiated again w.r.t. the weights (through
+    ``_PnPJacCov``), which is how the reference builds ``jac`` and its double-backward (``pnp_auto.py:124-134``)."""
+    @staticmethod
+    def forward(ctx, pts2d, jac):
+        ctx.save_for_backward(jac)
+        return jac.new_zeros(jac.shape[0], 6)
+
+    @staticmethod
+    def backward(ctx, g):
+        (jac,) = ctx.saved_tensors
+        return torch.einsum("bk,bknc->bnc", g, jac), None
+
+
 def diff_pnp_perturb(quat_xyz: Tensor, cam_K: Tensor, pts3d: Tensor, pts2d: Tensor, icov2: Tensor, with_cov: bool = True):
-    """Reference signature (``pnp_auto.py:86``): returns ``(info, right_update, cov)``.  ``right_update``
-    is identically zero in value, exactly like the reference's ``nll_update`` (``pnp_utils.py:118-122``);
-    ``info`` is non-zero where the Hessian was not SPD and got replaced by the identity."""
-    jac_cov = weighted_pnp_jac_wrt_pts2d(pts2d, quat_xyz, cam_K, pts3d, icov2, with_cov=True)
-    cov = jac_cov[1]
-    lead = pts3d.shape[:-2]
-    p3 = pts3d.detach().reshape((-1,) + tuple(pts3d.shape[-2:]))
-    B, N = p3.shape[:2]
-    _, _, flags = _jac_cov_forward(quat_xyz.detach().reshape(-1, 7), cam_K.detach().reshape(-1, 3, 3), p3,
-                                   _weights_as_bn2(icov2.detach().reshape((B,) + tuple(icov2.shape[len(lead):])), B, N),
-                                   pts2d.detach().expand(tuple(lead) + (N, 2)).reshape(B, N, 2))
+    """Reference signature (``pnp_auto.py:86-108``): returns ``(info, right_update, cov)``.
+
+    ``right_update`` is identically zero in value, exactly like the reference's ``nll_update`` (``pnp_utils.py:118-122``),
+    and carries the same gradient information w.r.t. ``pts2d``: ``autograd.grad(right_update, pts2d, g)`` returns
+    ``g^T jac`` with ``jac = W_k H^-1 J_k`` (``create_graph=True`` keeps it differentiable w.r.t. ``icov2``).  Its gradient
+    w.r.t. ``icov2`` itself (``-H^-1 r_k J_k`` in the reference) is not provided: it vanishes at the optimal operating
+    point the reference documents this function for (``pnp_auto.py:89``).
+    ``info`` is non-zero where the Hessian was not SPD and got replaced by the identity (``safe_cholesky``)."""
+    w, pose, K, p3, p2, lead, N = _flatten_inputs(pts2d, quat_xyz, cam_K, pts3d, icov2)
+    jac, cov, flags = _PnPJacCov.apply(w, pose, K, p3, p2.detach())
     info = (flags & nat.ST_HESS_NOT_SPD).reshape(lead)
-    update = cov.new_zeros(lead + (6,))
-    return info, update, (cov if with_cov else None)
+    update = _RightUpdate.apply(p2, jac).reshape(lead + (6,))
+    return info, update, (cov.reshape(lead + (6, 6)) if with_cov else None)

@@ -240,3 +240,42 @@ def test_pnp_jac_exact_hessian_away_from_optimum():
     from lc_b200.nll.pnp_auto import _jac_cov_forward
     j0, c0, _ = _jac_cov_forward(_cuda(z["in_pose"], dt), _cuda(z["in_K"], dt), _cuda(z["in_pts3d"], dt), W.detach())
     assert rel_err(c0.cpu().numpy(), z["ref_cov"]) > 1e-5
+
+
+def test_diff_pnp_perturb_contract():
+    """diff_pnp_perturb (pnp_auto.py:86-108): (info, right_update == 0, cov); right_update carries the gradient information the
+    reference extracts with autograd.grad(update, pts2d) (pnp_auto.py:124-134): row k of the Jacobian is jac[:, k], and with
+    create_graph=True the result stays differentiable w.r.t. the weights.  Checked against the reference-generated fixture."""
+    from lc_b200.nll.pnp_auto import diff_pnp_perturb
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "jacx_b3_n40.npz"))
+    dt = torch.float64
+    W = _cuda(z["in_W"], dt).requires_grad_(True)
+    p2 = _cuda(z["in_pts2d"], dt).requires_grad_(True)
+    info, upd, cov = diff_pnp_perturb(_cuda(z["in_pose"], dt), _cuda(z["in_K"], dt), _cuda(z["in_pts3d"], dt), p2, W, with_cov=True)
+    assert upd.shape == (3, 6) and float(upd.abs().max()) == 0.0 and upd.requires_grad
+    assert info.shape == (3,) and not info.any()
+    assert rel_err(cov.detach().cpu().numpy(), z["ref_cov"]) <= 2e-7
+    rows = [torch.autograd.grad(upd[:, k].sum(), p2, create_graph=True)[0] for k in range(6)]
+    jac = torch.stack(rows, 1)                                            # (B,6,N,2), the reference's vmapped loop
+    assert rel_err(jac.detach().cpu().numpy(), z["ref_jac"]) <= 2e-7
+    ((jac * _cuda(z["Gj"], dt)).sum() + (cov * _cuda(z["Gc"], dt)).sum()).backward()
+    assert rel_err(W.grad.cpu().numpy(), z["ref_gW"]) <= 1e-6
+    # un-batched form and with_cov=False
+    i1, u1, c1 = diff_pnp_perturb(_cuda(z["in_pose"][0], dt), _cuda(z["in_K"][0], dt), _cuda(z["in_pts3d"][0], dt),
+                                  _cuda(z["in_pts2d"][0], dt), _cuda(z["in_W"][0], dt), with_cov=False)
+    assert u1.shape == (6,) and c1 is None and i1.shape == ()
+
+
+def test_backward_twice_with_retain_graph():
+    """The reference's autograd graph can be back-propagated repeatedly under retain_graph=True; so can ours."""
+    from lc_b200.cov_mixed import Loss_cov_mixed
+    c = make_correspondences(3, 64, 5).to(torch.float32).to(device="cuda")
+    p3 = c.pts3d.clone().requires_grad_(True)
+    s = c.inv_std.clone().requires_grad_(True)
+    loss = Loss_cov_mixed(c.K, c.pose, p3, c.pts2d, s, c.valid, bbox_3d=c.bbox_3d).mean()
+    loss.backward(retain_graph=True)
+    g1 = p3.grad.clone()
+    loss.backward()
+    assert torch.allclose(p3.grad, 2 * g1)
