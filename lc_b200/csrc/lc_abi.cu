@@ -53,6 +53,8 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
     if (mode == (MODE_LM | MODE_LC) && a->weight_mode != LC_W_INV_STD)
         return fail(LC_E_BADARG, "solve_loss takes inverse std weights (weight_mode = LC_W_INV_STD)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // large N, many poses, planar slabs: the persistent pipelined kernel (one CTA per SM, two poses in flight, lc_persist.cu)
+    if (!(a->flags & LC_FLAG_FORCE_STREAMING) && persist_supported(*a, mode)) return check_launch(launch_persist_pose(*a, mode, st));
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && resident_supported(*a, mode)) return check_launch(launch_resident_pose(*a, mode, st));
     if (!(a->flags & LC_FLAG_FORCE_STREAMING)) {
         // Ragged batch padded beyond the resident limit (the test-time chain pads to the full map, test.py:106-119): poses with

@@ -57,6 +57,23 @@ __device__ __forceinline__ void rs_stage(double* v, unsigned lane) {
     }
 }
 
+// fp32 flavour for the fp32 point passes (one SHFL per exchanged value instead of two, no conversions): the per-thread
+// partial sums are fp32 already; the pairwise tree adds five roundings at 1/sqrt(nodes) weight, the totals of the warps are
+// then summed in fp64.
+template <int CUR, int OFF>
+__device__ __forceinline__ void rs_stage_f(float* v, unsigned lane) {
+    constexpr int H = half_up(CUR);
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float lo = v[j];
+        const float hi = (j + H < CUR) ? v[j + H] : 0.f;
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        v[j] = keep + __shfl_xor_sync(kFull, send, OFF);
+    }
+}
+
 template <int V>
 struct ReduceShape {
     static constexpr int c1 = half_up(V), c2 = half_up(c1), c3 = half_up(c2), c4 = half_up(c3), c5 = half_up(c4);
@@ -72,6 +89,16 @@ __device__ __forceinline__ void warp_reduce_scatter(double (&v)[V], unsigned lan
     rs_stage<S::c2, 4>(v, lane);
     rs_stage<S::c3, 2>(v, lane);
     rs_stage<S::c4, 1>(v, lane);
+}
+
+template <int V>
+__device__ __forceinline__ void warp_reduce_scatter_f(float (&v)[V], unsigned lane) {
+    using S = ReduceShape<V>;
+    rs_stage_f<V, 16>(v, lane);
+    rs_stage_f<S::c1, 8>(v, lane);
+    rs_stage_f<S::c2, 4>(v, lane);
+    rs_stage_f<S::c3, 2>(v, lane);
+    rs_stage_f<S::c4, 1>(v, lane);
 }
 
 template <int V>
@@ -104,6 +131,30 @@ __device__ __forceinline__ void block_reduce(double (&v)[V], double* red, double
     for (int k = 0; k < ReduceShape<V>::c5; ++k) {
         const int idx = orig_index<V>(k, lane);
         if (idx >= 0) dst[idx] = v[k];
+    }
+    __syncthreads();
+    if (NW > 1) {
+        for (int j = threadIdx.x; j < V; j += NT) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += red[w * V + j];
+            fin[j] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// Same for fp32 per-thread partial sums: fp32 tree inside the warp, fp64 across the warps.
+template <int V, int NT>
+__device__ __forceinline__ void block_reduce_f(float (&v)[V], double* red, double* fin) {
+    constexpr int NW = NT / 32;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warp_reduce_scatter_f<V>(v, lane);
+    double* dst = (NW == 1) ? fin : red + warp * V;
+#pragma unroll
+    for (int k = 0; k < ReduceShape<V>::c5; ++k) {
+        const int idx = orig_index<V>(k, lane);
+        if (idx >= 0) dst[idx] = static_cast<double>(v[k]);
     }
     __syncthreads();
     if (NW > 1) {

@@ -801,6 +801,235 @@ __device__ __forceinline__ void lc_six_warp(const lc_args& a, PoseShared& s, int
     LC_MARK(7);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident 6x6 sections (one warp, shuffles instead of shared-memory round trips).  Same math as lc_six_warp,
+// reorganised around the 24 bbox-corner rows r_m (accumulation basis, precomputed at pose setup by lc_rows_setup):
+//   C' = H'^-1 by six symmetric sweeps over the 21 packed entries held one per lane (pivots = LDL^T pivots = the
+//        leading-minor SPD test of safe_cholesky, pnp_utils.py:140-167)
+//   lane m < 24:  y_m = C' r_m,  g_m = G' y_m,  z_m = C' g_m
+//   forward :  v^C_m = r_m.y_m   v^M_m = y_m.g_m  (= r_m^T C'G'C' r_m, M' itself is never formed)   u_m = r_m.dtheta
+//   reverse :  Gbar = C' Mbar C' = sum_m wM_m y_m y_m^T        bbar = C' dthetabar = sum_m wU_m u_m y_m
+//              C' Cbar C' = sum_m [ wC_m y_m y_m^T + wM_m (y_m z_m^T + z_m y_m^T) ] + bbar dtheta^T      (Hbar = -that)
+//   i.e. every reverse quantity is a 24-term sum of per-lane outer products: two 24-value warp reduce-scatters.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sym_rc(int k, int& r, int& c) {   // packed index -> (r, c), r <= c
+    r = 0; c = k;
+    while (c >= 6 - r) { c -= 6 - r; ++r; }
+    c += r;
+}
+__device__ __forceinline__ int sym_at(int i, int j) { return i <= j ? sym_idx(i, j) : sym_idx(j, i); }
+
+// lanes 0..23 of one warp: bbox-corner Jacobian rows in the accumulation basis, [Rb(-[c_j]x) R^-1 | rows of Ut]
+// (cov_mixed.py:52-65).  Needs s.bbox, s.Rb, s.Ti.
+__device__ __forceinline__ void lc_rows_setup(PoseShared& s, int lane) {
+    if (lane < 24) {
+        const int j = lane / 3, r = lane % 3;
+        const double* c = s.bbox + 3 * j;
+        const double nC[9] = {0, c[2], -c[1], -c[2], 0, c[0], c[1], -c[0], 0};
+        double A3[3];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) A3[cc] = s.Rb[r * 3] * nC[cc] + s.Rb[r * 3 + 1] * nC[3 + cc] + s.Rb[r * 3 + 2] * nC[6 + cc];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) s.rows[lane * 6 + m] = A3[0] * s.Ti[m] + A3[1] * s.Ti[6 + m] + A3[2] * s.Ti[12 + m];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) s.rows[lane * 6 + 3 + m] = s.Ti[(3 + r) * 6 + 3 + m];
+    }
+}
+// one warp: pose setup of the LC phase (rotation, bases, bbox rows); ends with __syncwarp, caller adds the CTA barrier
+__device__ __forceinline__ void lc_pose_setup_warp(PoseShared& s, bool decouple_depth) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) { lc_pose_setup(s, decouple_depth); lc_pose_setup_acc(s); }
+    __syncwarp();
+    lc_rows_setup(s, lane);
+    __syncwarp();
+}
+
+// Called by one warp (all 32 lanes converged).  In: s.fin[0..48) = H', G' (packed), b'; s.rows.  Writes the loss / flags /
+// optional covariances and, when want_grads, s.cHL, s.cGL, s.bL.  The caller follows with a barrier.
+template <typename T, bool WITH_COV = true>
+__device__ __forceinline__ void lc_six_fast(const lc_args& a, PoseShared& s, int b, bool want_grads) {
+    const int lane = threadIdx.x & 31;
+    int r = 0, c = 0;
+    if (lane < kSym) sym_rc(lane, r, c);
+    LC_MARK(0);
+    // ---- C' = H'^-1: symmetric sweeps, lane k < 21 owns packed entry k = (r, c) ----
+    double A = lane < kSym ? s.fin[lane] : 1.0;
+    int info = 0;
+#pragma unroll 1
+    for (int p = 0; p < 6; ++p) {
+        const double d = __shfl_sync(kFull, A, sym_idx(p, p));
+        const double arp = __shfl_sync(kFull, A, sym_at(r, p)), apc = __shfl_sync(kFull, A, sym_at(p, c));
+        if (!(d > 0.0) || isinf(d)) { info = p + 1; break; }   // uniform: every lane sees the same pivot
+        const double ip = fast_rcp(d);
+        if (r == p && c == p) A = -ip;
+        else if (r == p || c == p) A = A * ip;
+        else A = fma(-arp * ip, apc, A);
+    }
+    double Crc = -A;
+    LC_MARK(1);
+    if (info != 0) {
+        // non-SPD -> H_ref := I (pnp_utils.py:140-158), i.e. C' = Tm Tm^T
+        if (lane == 0) s.flag |= LC_ST_HESS_NOT_SPD;
+        Crc = 0.0;
+        for (int k = 0; k < 6; ++k) Crc = fma(s.Tm[r * 6 + k], s.Tm[c * 6 + k], Crc);
+    }
+    if (lane < kSym) { s.C[r * 6 + c] = Crc; s.C[c * 6 + r] = Crc; }
+    __syncwarp();
+    // ---- per bbox-corner coordinate (lane m < 24): y = C' r, and dtheta = C' b' on lanes 24..29 ----
+    const double* bacc = s.fin + 42;
+    double row[6], y[6], g[6], z[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { row[i] = 0.0; y[i] = 0.0; g[i] = 0.0; z[i] = 0.0; }
+    if (lane < 24) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) row[i] = s.rows[lane * 6 + i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v = fma(s.C[i * 6 + j], row[j], v);
+            y[i] = v;
+        }
+    } else if (lane < 30) {
+        const int i = lane - 24;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v = fma(s.C[i * 6 + j], bacc[j], v);
+        s.dth[i] = v;
+        s.bv[i] = bacc[i];
+    }
+    __syncwarp();
+    LC_MARK(2);
+    double vc = 1.0, vm = 1.0, uu = 0.0;
+    if (lane < 24) {
+        vc = 0.0; vm = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v = fma(s.fin[21 + sym_at(i, j)], y[j], v);
+            g[i] = v;
+            vc = fma(row[i], y[i], vc); uu = fma(row[i], s.dth[i], uu);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) vm = fma(y[i], g[i], vm);
+        if (want_grads) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v = fma(s.C[i * 6 + j], g[j], v);
+                z[i] = v;
+            }
+        }
+    }
+    LC_MARK(3);
+    // ---- prior variance, propagated variance, linear term per corner; the scalar loss (cov_mixed.py:68-89, 134-149) ----
+    const bool goodC = __all_sync(kFull, vc > 0.0), goodM = __all_sync(kFull, vm > 0.0);
+    if (lane == 0) s.flag |= (goodC ? 0 : LC_ST_PRIOR_NOT_GOOD) | (goodM ? 0 : LC_ST_COV_NOT_GOOD);
+    // corner sums: lanes 3j, 3j+1, 3j+2 -> lane 3j
+    const double wCj = vc + __shfl_down_sync(kFull, vc, 1) + __shfl_down_sync(kFull, vc, 2);
+    const double wMj = vm + __shfl_down_sync(kFull, vm, 1) + __shfl_down_sync(kFull, vm, 2);
+    const double u2 = uu * uu;
+    const double wUj = u2 + __shfl_down_sync(kFull, u2, 1) + __shfl_down_sync(kFull, u2, 2);
+    // lane L < 24: group gq = L / 8 (0 prior, 1 cov_err, 2 lin), corner j = L % 8: fetch that corner's sum from lane 3j
+    const int gq = lane >> 3, j8 = lane & 7;
+    const double sC = __shfl_sync(kFull, wCj, 3 * j8), sM = __shfl_sync(kFull, wMj, 3 * j8), sU = __shfl_sync(kFull, wUj, 3 * j8);
+    const double xg = gq == 0 ? sC : (gq == 1 ? sM : sU);
+    const bool live = gq == 0 ? goodC : (gq == 1 ? goodM : (gq == 2 && xg > 0.0));
+    const double rs = live ? rsqrt(xg) : (gq == 2 ? 0.0 : 1.0);
+    const double term = live ? xg * rs : (gq < 2 ? 1.0 : 0.0);   // sqrt term of this lane's (group, corner); rs = its reciprocal
+    double sum = term;
+    sum += __shfl_xor_sync(kFull, sum, 1);
+    sum += __shfl_xor_sync(kFull, sum, 2);
+    sum += __shfl_xor_sync(kFull, sum, 4);
+    const double prior = 0.125 * __shfl_sync(kFull, sum, 0), cov_err = 0.125 * __shfl_sync(kFull, sum, 8),
+                 lin = 0.125 * __shfl_sync(kFull, sum, 16);
+    const double ip = fast_rcp(prior);
+    const double go = a.grad_scale * (a.grad_out.ptr ? ld<T>(a.grad_out, b * a.grad_out.stride[0]) : 1.0);
+    const double g_p = go * (ip - 0.5 * (cov_err + lin) * ip * ip);
+    const double g_c = go * 0.5 * ip;
+    if (lane == 0) {
+        const double loss = log(prior) + 0.5 * (cov_err + lin) * ip;
+        if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], loss);
+        if (a.lc_flags) a.lc_flags[b] = s.flag;
+        if (a.loss_sum) { atomicAdd(a.loss_sum, loss); atomicAdd(a.loss_sum + 1, 1.0); }
+    }
+    // reverse weights of this lane's (group, corner), then per corner-coordinate lane m: its corner's three weights
+    const double wq = gq == 0 ? (goodC ? g_p * 0.0625 * rs : 0.0) : (gq == 1 ? (goodM ? g_c * 0.0625 * rs : 0.0) : g_c * 0.125 * rs);
+    const int jc = (lane < 24 ? lane : 0) / 3;
+    const double wC = __shfl_sync(kFull, wq, jc), wM = __shfl_sync(kFull, wq, 8 + jc), wU = __shfl_sync(kFull, wq, 16 + jc);
+    if (WITH_COV && (a.cov.ptr || a.update_cov.ptr)) {
+        // reference-basis covariances on request: S_ref = Tm^-1 S' Tm^-T with M' = C' G' C' formed explicitly (not on the training path)
+        for (int e = lane; e < 36; e += 32) s.G[e] = s.fin[21 + sym_at(e / 6, e % 6)];
+        __syncwarp();
+        mm6_warp(s.C, s.G, s.T1, lane);
+        __syncwarp();
+        mm6_warp(s.T1, s.C, s.M, lane);
+        __syncwarp();
+        for (int e = lane; e < 36; e += 32) {
+            const int rr = e / 6, cc = e % 6;
+            double vC = 0.0, vM = 0.0;
+            for (int i = 0; i < 6; ++i) {
+                double wc = 0.0, wm = 0.0;
+                for (int k = 0; k < 6; ++k) { wc = fma(s.C[i * 6 + k], s.Ti[cc * 6 + k], wc); wm = fma(0.5 * (s.M[i * 6 + k] + s.M[k * 6 + i]), s.Ti[cc * 6 + k], wm); }
+                vC = fma(s.Ti[rr * 6 + i], wc, vC); vM = fma(s.Ti[rr * 6 + i], wm, vM);
+            }
+            if (a.cov.ptr) st<T>(a.cov, b * a.cov.stride[0] + rr * a.cov.stride[1] + cc * a.cov.stride[2], vC);
+            if (a.update_cov.ptr) st<T>(a.update_cov, b * a.update_cov.stride[0] + rr * a.update_cov.stride[1] + cc * a.update_cov.stride[2], vM);
+        }
+    }
+    LC_MARK(4);
+    if (!want_grads) return;
+
+    // ---- reverse: 24-term sums of per-lane outer products ----
+    const bool lv = lane < 24;
+    const double cw = lv ? wC : 0.0, mw = lv ? wM : 0.0, uw = lv ? wU * uu : 0.0;
+    double acc[24];
+    // (i) Gbar packed (off-diagonals doubled) and bbar[0..3)
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) { acc[k] = (i == j ? mw : 2.0 * mw) * (y[i] * y[j]); ++k; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[21 + i] = uw * y[i];
+        warp_reduce_scatter<24>(acc, lane);
+        const int idx = orig_index<24>(0, lane);
+        __syncwarp();
+        if (idx >= 0 && idx < kSym) s.cGL[idx] = acc[0];
+        else if (idx >= kSym) s.bL[idx - kSym] = acc[0];
+    }
+    LC_MARK(5);
+    // (ii) C' Cbar C' without the bbar dtheta^T term, packed (off-diagonals doubled), and bbar[3..6)
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) {
+                const double v = fma(cw, y[i] * y[j], mw * fma(y[i], z[j], z[i] * y[j]));
+                acc[k] = i == j ? v : 2.0 * v;
+                ++k;
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) acc[21 + i] = uw * y[3 + i];
+        warp_reduce_scatter<24>(acc, lane);
+        const int idx = orig_index<24>(0, lane);
+        if (idx >= 0 && idx < kSym) s.cHL[idx] = acc[0];
+        else if (idx >= kSym) s.bL[3 + idx - kSym] = acc[0];
+    }
+    __syncwarp();
+    LC_MARK(6);
+    // cHL = -(C' Cbar C' + sym part of bbar dtheta^T), zero when H was replaced (torch.where(cond, eye, H): no gradient into H)
+    if (lane < kSym) {
+        const double bd = r == c ? s.bL[r] * s.dth[r] : fma(s.bL[r], s.dth[c], s.bL[c] * s.dth[r]);
+        s.cHL[lane] = info == 0 ? -(s.cHL[lane] + bd) : 0.0;
+    }
+    LC_MARK(7);
+}
+
 // every launch site records the kernel it dispatched (lc_abi.cu): lc_b200_last_launch_count() / lc_b200_last_kernels() report
 // what actually ran, not what the caller expected
 void note_kernel(const char* fmt, ...);
@@ -811,6 +1040,8 @@ int launch_stream_jac(const lc_args& a, bool bwd, cudaStream_t st);
 bool resident_supported(const lc_args& a, int mode);
 int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st, int cap = 0);
 int resident_split_capacity(const lc_args& a, int mode);
+bool persist_supported(const lc_args& a, int mode);
+int launch_persist_pose(const lc_args& a, int mode, cudaStream_t st);
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
 int launch_decode(const lc_decode_args& d, cudaStream_t st);
 int launch_encode(const lc_encode_args& d, cudaStream_t st);

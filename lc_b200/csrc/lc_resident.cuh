@@ -228,12 +228,123 @@ struct DirectSink {      // gradients written to the strided views of lc_args
     }
 };
 
+// Per-point fp32 geometry shared by passes 3 and 4: left-basis Jacobian rows (depth-decoupled accumulation basis, see
+// lc_phase_res) and the robust weights of robust_weights_cov (cov_mixed.py:27-39).
+struct PointConsts {
+    float t0, t1, t2, k00, k01, k10, k11, uc, vc, d0, d1, sq0, sq1;
+};
+__device__ __forceinline__ PointConsts make_point_consts(const PoseShared& s, float d0, float d1, float sq0, float sq1) {
+    PointConsts c;
+    c.t0 = static_cast<float>(s.t[0]); c.t1 = static_cast<float>(s.t[1]); c.t2 = static_cast<float>(s.t[2]);
+    c.k00 = static_cast<float>(s.K[0]); c.k01 = static_cast<float>(s.K[1]); c.k10 = static_cast<float>(s.K[3]); c.k11 = static_cast<float>(s.K[4]);
+    c.uc = static_cast<float>(s.t[0] / s.t[2]); c.vc = static_cast<float>(s.t[1] / s.t[2]);
+    c.d0 = d0; c.d1 = d1; c.sq0 = sq0; c.sq1 = sq1;
+    return c;
+}
+__device__ __forceinline__ void point_terms_f(const PointConsts& pc, float q0, float q1, float q2, const float (&ec)[2], const float (&sk)[2],
+                                              float (&J)[2][6], float (&sg)[2], float (&del)[2], float (&w)[2]) {
+    const float P0 = q0 + pc.t0, P1 = q1 + pc.t1, P2 = q2 + pc.t2;
+    const float iz = __fdividef(1.f, P2);
+    const float u0 = P0 * iz, v0 = P1 * iz;
+    const float du0 = fmaf(pc.uc, q2, -q0) * iz, dv0 = fmaf(pc.vc, q2, -q1) * iz;   // uvc - uv0
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float ka = c ? pc.k10 : pc.k00, kb = c ? pc.k11 : pc.k01;
+        const float e0 = ka * iz, e1 = kb * iz, e2 = -fmaf(ka, u0, kb * v0) * iz;
+        J[c][0] = fmaf(q1, e2, -q2 * e1);
+        J[c][1] = fmaf(q2, e0, -q0 * e2);
+        J[c][2] = fmaf(q0, e1, -q1 * e0);
+        J[c][3] = e0; J[c][4] = e1; J[c][5] = fmaf(ka, du0, kb * dv0) * iz;
+        const float dc = c ? pc.d1 : pc.d0, sq = c ? pc.sq1 : pc.sq0;
+        const float av = fabsf(ec[c]);
+        sg[c] = av > dc ? dc * (2.f * av - dc) : av * av;
+        del[c] = sq * rsqrtf(sg[c] + 1e-6f);
+        w[c] = sk[c] > del[c] ? del[c] * (2.f * sk[c] - del[c]) : sk[c] * sk[c];
+    }
+}
+
+// pass 4 (fp32), one point per thread and iteration, any strides: per-coordinate adjoints and the three input
+// gradients.  Also the fallback of the vectorised phase (lc_vec.cuh) for poses with a general K row 2 or a clamped depth.
+template <int NT, class WSrc, class Sink, bool TM>
+__device__ __forceinline__ void lc_pass4_scalar(const lc_args& a, PoseShared& s, const ResLayout& l, int n, float d0, float d1, float sq0, float sq1,
+                                                const WSrc& wsrc, Sink& sink, const XAcc<TM>& xs) {
+    const PointConsts pc = make_point_consts(s, d0, d1, sq0, sq1);
+    const float t0 = pc.t0, t1 = pc.t1, t2 = pc.t2;
+    auto point_terms = [&](int i, float q0, float q1, float q2, float (&J)[2][6], float (&ec)[2], float (&sk)[2], float (&sg)[2], float (&del)[2],
+                           float (&w)[2]) {
+        ec[0] = l.B0[i]; ec[1] = l.B1[i];
+        wsrc.get(i, sk[0], sk[1]);
+        point_terms_f(pc, q0, q1, q2, ec, sk, J, sg, del, w);
+    };
+    {
+        float cH[kSym], cG[kSym], bL[6];
+#pragma unroll
+        for (int k = 0; k < kSym; ++k) { cH[k] = static_cast<float>(s.cHL[k]); cG[k] = static_cast<float>(s.cGL[k]); }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) bL[k] = static_cast<float>(s.bL[k]);
+        const float K0 = static_cast<float>(s.K[0]), K1 = static_cast<float>(s.K[1]), K2 = static_cast<float>(s.K[2]);
+        const float K3 = static_cast<float>(s.K[3]), K4 = static_cast<float>(s.K[4]), K5 = static_cast<float>(s.K[5]);
+        const float K6 = static_cast<float>(s.K[6]), K7 = static_cast<float>(s.K[7]), K8 = static_cast<float>(s.K[8]);
+        float Rf[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
+        LC_POINT_LOOP(TM, NT, n) {
+            const bool live = !TM || i < n;
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+            xs.ld(i, k, live, q0, q1, q2);
+            if (!live) continue;
+            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
+            point_terms(i, q0, q1, q2, J, ec, sk, sg, del, w);
+            float ecb[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float qh = 0.f, qg = 0.f, lb = 0.f;
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    lb = fmaf(J[c][r], bL[r], lb);
+#pragma unroll
+                    for (int cc = r; cc < 6; ++cc) {
+                        const float pp = J[c][r] * J[c][cc];
+                        qh = fmaf(cH[k], pp, qh);
+                        qg = fmaf(cG[k], pp, qg);
+                        ++k;
+                    }
+                }
+                const float Wbar = qh + 2.f * w[c] * sg[c] * qg + ec[c] * lb;
+                const float sigbar = w[c] * w[c] * qg;
+                sink.weight_grad(i, c, Wbar * (sk[c] > del[c] ? 2.f * del[c] : 2.f * sk[c]), sk[c]);
+                const float dc = c ? d1 : d0;
+                const float av = fabsf(ec[c]);
+                const float sgn = (ec[c] > 0.f) ? 1.f : ((ec[c] < 0.f) ? -1.f : 0.f);
+                ecb[c] = sigbar * (av > dc ? 2.f * dc : 2.f * av) * sgn;
+                sink.pts2d_grad(i, c, ecb[c]);
+            }
+            if (sink.want_pts3d()) {
+                // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
+                const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
+                const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
+                const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
+                const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
+                const bool act = KP2 >= 0.1f;
+                const float iz = __fdividef(1.f, act ? KP2 : 0.1f);
+                const float pr0 = act ? KP0 * iz : 0.f, pr1 = act ? KP1 * iz : 0.f;   // proj * [z >= 0.1]
+                const float gP0 = (fmaf(-pr0, K6, K0) * ecb[0] + fmaf(-pr1, K6, K3) * ecb[1]) * iz;
+                const float gP1 = (fmaf(-pr0, K7, K1) * ecb[0] + fmaf(-pr1, K7, K4) * ecb[1]) * iz;
+                const float gP2 = (fmaf(-pr0, K8, K2) * ecb[0] + fmaf(-pr1, K8, K5) * ecb[1]) * iz;
+                sink.pts3d_grad(i, -(Rf[0] * gP0 + Rf[3] * gP1 + Rf[6] * gP2), -(Rf[1] * gP0 + Rf[4] * gP1 + Rf[7] * gP2),
+                                -(Rf[2] * gP0 + Rf[5] * gP1 + Rf[8] * gP2));
+            }
+        }
+    }
+}
+
 template <int NT, class WSrc, class Sink, bool TM>
 __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, const WSrc& wsrc, Sink& sink,
                                              const XAcc<TM>& xs) {
     const int tid = threadIdx.x;
     { LC_TIC(tq1);
-    if (tid == 0) { lc_pose_setup(s, true); lc_pose_setup_acc(s); }
+    if (tid < 32) lc_pose_setup_warp(s, true);
     __syncthreads();
     LC_TOC(tq1, 3); }
     LC_TIC(tq2);
@@ -366,74 +477,13 @@ __device__ __forceinline__ void lc_phase_res(const lc_args& a, PoseShared& s, co
     }
     LC_TOC(tq2, 4);
     { LC_TIC(tq3);
-    if (tid < 32) lc_six_warp<float>(a, s, b, sink.want_any());
+    if (tid < 32) lc_six_fast<float>(a, s, b, sink.want_any());
     __syncthreads();
     if (!sink.want_any()) return;
     LC_TOC(tq3, 5); }
     LC_TIC(tq4);
 
-    // pass 4 (fp32): per-coordinate adjoints and the three input gradients
-    {
-        float cH[kSym], cG[kSym], bL[6];
-#pragma unroll
-        for (int k = 0; k < kSym; ++k) { cH[k] = static_cast<float>(s.cHL[k]); cG[k] = static_cast<float>(s.cGL[k]); }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) bL[k] = static_cast<float>(s.bL[k]);
-        const float K0 = static_cast<float>(s.K[0]), K1 = static_cast<float>(s.K[1]), K2 = static_cast<float>(s.K[2]);
-        const float K3 = static_cast<float>(s.K[3]), K4 = static_cast<float>(s.K[4]), K5 = static_cast<float>(s.K[5]);
-        const float K6 = static_cast<float>(s.K[6]), K7 = static_cast<float>(s.K[7]), K8 = static_cast<float>(s.K[8]);
-        float Rf[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Rf[k] = static_cast<float>(s.R[k]);
-        LC_POINT_LOOP(TM, NT, n) {
-            const bool live = !TM || i < n;
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-            xs.ld(i, k, live, q0, q1, q2);
-            if (!live) continue;
-            float J[2][6], ec[2], sk[2], sg[2], del[2], w[2];
-            point_terms(i, q0, q1, q2, J, ec, sk, sg, del, w);
-            float ecb[2];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                float qh = 0.f, qg = 0.f, lb = 0.f;
-                int k = 0;
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    lb = fmaf(J[c][r], bL[r], lb);
-#pragma unroll
-                    for (int cc = r; cc < 6; ++cc) {
-                        const float pp = J[c][r] * J[c][cc];
-                        qh = fmaf(cH[k], pp, qh);
-                        qg = fmaf(cG[k], pp, qg);
-                        ++k;
-                    }
-                }
-                const float Wbar = qh + 2.f * w[c] * sg[c] * qg + ec[c] * lb;
-                const float sigbar = w[c] * w[c] * qg;
-                sink.weight_grad(i, c, Wbar * (sk[c] > del[c] ? 2.f * del[c] : 2.f * sk[c]), sk[c]);
-                const float dc = c ? d1 : d0;
-                const float av = fabsf(ec[c]);
-                const float sgn = (ec[c] > 0.f) ? 1.f : ((ec[c] < 0.f) ? -1.f : 0.f);
-                ecb[c] = sigbar * (av > dc ? 2.f * dc : 2.f * av) * sgn;
-                sink.pts2d_grad(i, c, ecb[c]);
-            }
-            if (sink.want_pts3d()) {
-                // gX = -R^T (dproj/dP)^T ecbar,  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z >= 0.1]) / max(z, 0.1)
-                const float P0 = q0 + t0, P1 = q1 + t1, P2 = q2 + t2;
-                const float KP0 = fmaf(K0, P0, fmaf(K1, P1, K2 * P2));
-                const float KP1 = fmaf(K3, P0, fmaf(K4, P1, K5 * P2));
-                const float KP2 = fmaf(K6, P0, fmaf(K7, P1, K8 * P2));
-                const bool act = KP2 >= 0.1f;
-                const float iz = __fdividef(1.f, act ? KP2 : 0.1f);
-                const float pr0 = act ? KP0 * iz : 0.f, pr1 = act ? KP1 * iz : 0.f;   // proj * [z >= 0.1]
-                const float gP0 = (fmaf(-pr0, K6, K0) * ecb[0] + fmaf(-pr1, K6, K3) * ecb[1]) * iz;
-                const float gP1 = (fmaf(-pr0, K7, K1) * ecb[0] + fmaf(-pr1, K7, K4) * ecb[1]) * iz;
-                const float gP2 = (fmaf(-pr0, K8, K2) * ecb[0] + fmaf(-pr1, K8, K5) * ecb[1]) * iz;
-                sink.pts3d_grad(i, -(Rf[0] * gP0 + Rf[3] * gP1 + Rf[6] * gP2), -(Rf[1] * gP0 + Rf[4] * gP1 + Rf[7] * gP2),
-                                -(Rf[2] * gP0 + Rf[5] * gP1 + Rf[8] * gP2));
-            }
-        }
-    }
+    lc_pass4_scalar<NT>(a, s, l, n, d0, d1, sq0, sq1, wsrc, sink, xs);
 #ifdef LC_TIMING
     __syncthreads();
 #endif

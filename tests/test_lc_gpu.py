@@ -196,14 +196,18 @@ def test_headline_size_properties():
     assert rel_err(pp["g_pts3d"].cpu().numpy(), part["g_pts3d"][:, perm].cpu().numpy()) <= 1e-5
 
 
-def test_tma_and_cp_async_staging_agree():
+def test_tma_and_cp_async_staging_agree(monkeypatch):
     """Planar 16-byte aligned inputs are staged by TMA bulk copies, everything else by cp.async; same results.
     Covers: planar aligned (TMA for both arrays), AoS (cp.async), planar but N % 4 != 0 and a misaligned base
-    pointer (cp.async), and the mixed case (planar pts3d + AoS pts2d)."""
+    pointer (cp.async), and the mixed case (planar pts3d + AoS pts2d).  With the scalar point loops (LC_B200_NO_VEC) the
+    staging path must not change a single bit; the vectorised point loops that planar weights / gradients select sum in a
+    different order and agree to fp32 rounding."""
     from lc_b200.cov_mixed import loss_fwd_bwd
     from lc_b200.fused import solve_and_loss
+    from lc_b200 import _native as nat
     for N in (512, 514):
         c = make_correspondences(5, N, 61).to(torch.float32).to(device="cuda")
+        monkeypatch.setenv("LC_B200_NO_VEC", "1")
         ref = loss_fwd_bwd(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)                       # AoS
         a = loss_fwd_bwd(c.K, c.pose, planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std), None, c.bbox_3d)
         m = loss_fwd_bwd(c.K, c.pose, planar_view(c.pts3d), c.pts2d, planar_view(c.inv_std), None, c.bbox_3d)   # mixed
@@ -218,6 +222,15 @@ def test_tma_and_cp_async_staging_agree():
         f0 = solve_and_loss(c.K, c.start, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d)
         f1 = solve_and_loss(c.K, c.start, planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std), None, c.bbox_3d)
         assert torch.equal(f0["states"], f1["states"]) and torch.equal(f0["loss"], f1["loss"])
+        monkeypatch.delenv("LC_B200_NO_VEC")
+        v = loss_fwd_bwd(c.K, c.pose, planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std), None, c.bbox_3d)
+        vec_ran = b"vec4" in nat.lib().lc_b200_last_kernels()
+        assert vec_ran == (N % 4 == 0)
+        assert rel_err(v["loss"].cpu().numpy()[:, None], ref["loss"].cpu().numpy()[:, None]) <= 2e-6
+        for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
+            assert rel_err(v[k].cpu().numpy(), ref[k].cpu().numpy()) <= 2e-5, k
+        f2 = solve_and_loss(c.K, c.start, planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std), None, c.bbox_3d)
+        assert torch.equal(f2["iters"], f0["iters"]) and (f2["states"] - f0["states"]).abs().max() <= 2e-6 * f0["states"].abs().max()
 
 
 def test_pnp_jac_exact_hessian_away_from_optimum():

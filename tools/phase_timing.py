@@ -50,6 +50,16 @@ def run(pipeline):
     for _ in range(3):
         nat.call(mode, a, X.device)
     torch.cuda.synchronize()
+    if b"persist" in nat.lib().lc_b200_last_kernels():
+        t = trace.reshape(-1)[: 148 * 64].reshape(148, 64).cpu().numpy().mean(0)
+        names = ["-", "LM pass", "LC pass 1", "LC pass 2", "LC pass 3", "LC pass 4", "LC pass 4 (general)", "-"]
+        print(f"{pipeline} persistent kernel, mean cycles per CTA (= per SM, ~6.9 poses): total {t[26]:.0f}")
+        print("  workers (thread 0):  " + ", ".join(f"{n} {t[k]:.0f}" for k, n in enumerate(names) if t[k] > 0) + f", waiting for the serial warp {t[8]:.0f}")
+        print("  serial warp (lane 0): after " + ", after ".join(f"{n} {t[16 + k]:.0f}" for k, n in enumerate(names) if t[16 + k] > 0)
+              + f", next-pose setup {t[25]:.0f}, waiting for the workers {t[24]:.0f}")
+        if t[27] > 0:
+            print(f"  6x6 section executed twice in a row (LC_TIMING_SIX2): first {t[27]:.0f}, second {t[28]:.0f} cycles per CTA")
+        return
     t = trace.reshape(B, -1)[:, :8].cpu().numpy()
     names = ["stage", "LM passes", "LM advance", "LC setup", "LC pass1-3", "six fwd+bwd", "LC pass 4", "total"]
     tot = t[:, 7].mean()
