@@ -95,7 +95,7 @@ typedef struct lc_args {
     lc_view valid;    /* (B,N) or NULL */
     lc_view bbox;     /* (B,8,3) */
     lc_view grad_out; /* (B) upstream d/d loss_b, or NULL (= 1) */
-    const int32_t* n_points; /* (B) valid correspondences per pose, or NULL (= N) */
+    const int32_t* n_points; /* (B) valid correspondences per pose, or NULL (= N); the gradient slots i >= n_points[b] are written as 0 */
 
     /* outputs (NULL = not wanted) */
     lc_view loss;      /* (B) */

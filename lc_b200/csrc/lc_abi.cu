@@ -53,6 +53,8 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
     if (mode == (MODE_LM | MODE_LC) && a->weight_mode != LC_W_INV_STD)
         return fail(LC_E_BADARG, "solve_loss takes inverse std weights (weight_mode = LC_W_INV_STD)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // sparse keypoints (N <= 32): one thread per pose, the serial 6x6 / trust-region sections of 32 poses run in parallel (lc_tiny.cu)
+    if (!(a->flags & LC_FLAG_FORCE_STREAMING) && a->N <= kTinyMaxN) return check_launch(launch_tiny_pose(*a, mode, st));
     // large N, many poses, planar slabs: the persistent pipelined kernel (one CTA per SM, two poses in flight, lc_persist.cu)
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && persist_supported(*a, mode)) return check_launch(launch_persist_pose(*a, mode, st));
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && resident_supported(*a, mode)) return check_launch(launch_resident_pose(*a, mode, st));

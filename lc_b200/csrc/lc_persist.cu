@@ -440,7 +440,9 @@ static bool device_info(DevInfo& d) {
 }
 
 bool persist_supported(const lc_args& a, int mode) {
-    if (const char* e = getenv("LC_B200_PERSIST")) { if (e[0] == '0') return false; }
+    // opt-in (LC_B200_PERSIST=1): measured on B200 at B = 1024 x N = 4096 the CTA-per-pose kernels are faster (profiles/README.md)
+    const char* e = getenv("LC_B200_PERSIST");
+    if (!e || e[0] != '1') return false;
     if (a.dtype != LC_F32 || a.N < 2048) return false;
     if (a.weight_mode != LC_W_ICOV_DIAG && a.weight_mode != LC_W_INV_STD) return false;
     if (!planar_ok(a.pts3d, a.N) || !planar_ok(a.weights, a.N)) return false;

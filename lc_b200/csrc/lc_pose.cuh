@@ -341,8 +341,8 @@ __device__ inline void angle_axis_to_quat(const double* aa, double* q) {
 
 // LM epilogue (thread 0): ceres.cpp:134-144 writes the state back only when valid; cer_solver.py:51-52 keeps
 // `start` otherwise.  s.pose becomes the pose the LC phase runs at (rounded to the I/O type like the reference).
-template <typename T>
-__device__ inline void lm_write_result(const lc_args& a, PoseShared& s, int b, int n, bool solved) {
+template <typename T, class PS = PoseShared>
+__device__ inline void lm_write_result(const lc_args& a, PS& s, int b, int n, bool solved) {
     LmState& L = s.lm;
     if (solved) {
         double q[4];
@@ -1042,6 +1042,8 @@ int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st, int cap = 
 int resident_split_capacity(const lc_args& a, int mode);
 bool persist_supported(const lc_args& a, int mode);
 int launch_persist_pose(const lc_args& a, int mode, cudaStream_t st);
+int launch_tiny_pose(const lc_args& a, int mode, cudaStream_t st);
+constexpr int kTinyMaxN = 32;   // N <= this: one THREAD per pose (lc_tiny.cu)
 int launch_dense(const lc_dense_args& d, cudaStream_t st);
 int launch_decode(const lc_decode_args& d, cudaStream_t st);
 int launch_encode(const lc_encode_args& d, cudaStream_t st);

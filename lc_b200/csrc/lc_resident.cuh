@@ -276,6 +276,11 @@ __device__ __forceinline__ void lc_pass4_scalar(const lc_args& a, PoseShared& s,
         wsrc.get(i, sk[0], sk[1]);
         point_terms_f(pc, q0, q1, q2, ec, sk, J, sg, del, w);
     };
+    // gradient slots of the padding beyond n (ragged batches): defined, zero
+    for (int i = n + static_cast<int>(threadIdx.x); i < a.N; i += NT) {
+        for (int c = 0; c < 2; ++c) { sink.weight_grad(i, c, 0.f, 0.f); sink.pts2d_grad(i, c, 0.f); }
+        if (sink.want_pts3d()) sink.pts3d_grad(i, 0.f, 0.f, 0.f);
+    }
     {
         float cH[kSym], cG[kSym], bL[6];
 #pragma unroll

@@ -7,6 +7,11 @@
 
 #include "lc_vec.cuh"
 
+// the planar-weights LM pass (lm_eval_pass_planar) in the vectorised CTA-per-pose kernels: 0 = keep the strided pass
+#ifndef LC_RES_PLANAR_LM
+#define LC_RES_PLANAR_LM 0
+#endif
+
 namespace lc {
 
 // TM = true: the model points live in tensor memory (lc_resident.cuh: XAcc), shared memory holds only x -> ec.
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             for (;;) {
                 const int kind = L.ctl;
                 { LC_TIC(tq2);
-                if (VEC) {
+                if (VEC && LC_RES_PLANAR_LM) {
                     if (kind == CTL_EVAL_COST) {
                         if (wgen) lm_eval_pass_planar<NT, false, true>(a, s, l, b, n, sanitize);
                         else lm_eval_pass_planar<NT, false, false>(a, s, l, b, n, sanitize);

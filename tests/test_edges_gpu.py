@@ -134,10 +134,14 @@ def test_loss_kernel_with_ragged_n_points_in_the_tensor_memory_range():
     B = len(npts)
     c = make_correspondences(B, N, 9).to(torch.float32).to(device="cuda")
 
-    def run():
+    def run(planar=False):
         loss = torch.empty(B, device="cuda")
-        g3, gs = torch.zeros(B, N, 3, device="cuda"), torch.zeros(B, N, 2, device="cuda")
-        a = nat.make_args(B, N, torch.float32, K=c.K, pose=c.pose, pts3d=c.pts3d, pts2d=c.pts2d, weights=c.inv_std, bbox=c.bbox_3d,
+        # outputs start as NaN: the kernels must define every slot, including the padding beyond n_points (zeros)
+        g3, gs = torch.full((B, N, 3), float("nan"), device="cuda"), torch.full((B, N, 2), float("nan"), device="cuda")
+        X, x, w = c.pts3d, c.pts2d, c.inv_std
+        if planar:   # the layout of the dense call site: takes the vectorised kernels
+            X, x, w, g3, gs = planar_view(X), planar_view(x), planar_view(w), planar_view(g3), planar_view(gs)
+        a = nat.make_args(B, N, torch.float32, K=c.K, pose=c.pose, pts3d=X, pts2d=x, weights=w, bbox=c.bbox_3d,
                           n_points=torch.tensor(npts, dtype=torch.int32, device="cuda"), loss=loss, g_pts3d=g3, g_weights=gs)
         nat.call("lc_b200_loss_fwd_bwd", a, c.K.device)
         torch.cuda.synchronize()
@@ -150,10 +154,14 @@ def test_loss_kernel_with_ragged_n_points_in_the_tensor_memory_range():
         assert abs(loss[b].item() - o["loss"][0].item()) <= 2e-6 * max(1.0, abs(o["loss"][0].item())), n
         assert rel_err(g3[b:b + 1, :n].cpu().numpy(), o["g_pts3d"].cpu().numpy()) <= 2e-5, n
         assert rel_err(gs[b:b + 1, :n].cpu().numpy(), o["g_inv_std"].cpu().numpy()) <= 2e-5, n
-        assert (g3[b, n:] == 0).all() and (gs[b, n:] == 0).all()          # slots beyond n_points are not touched
+        assert (g3[b, n:] == 0).all() and (gs[b, n:] == 0).all()          # slots beyond n_points are written as zeros
     os.environ["LC_B200_TMEM"] = "0"
     try:
         loss0, g30, gs0 = run()
     finally:
         del os.environ["LC_B200_TMEM"]
     assert torch.allclose(loss, loss0, rtol=2e-6) and rel_err(g3.cpu().numpy(), g30.cpu().numpy()) <= 2e-5
+    lossv, g3v, gsv = run(planar=True)
+    assert b"vec4" in nat.lib().lc_b200_last_kernels()
+    assert torch.allclose(loss, lossv, rtol=2e-6) and rel_err(g3v.cpu().numpy(), g3.cpu().numpy()) <= 2e-5
+    assert rel_err(gsv.cpu().numpy(), gs.cpu().numpy()) <= 2e-5 and not torch.isnan(g3v).any() and not torch.isnan(gsv).any()
