@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             for (;;) {
                 const int kind = L.ctl;
                 { LC_TIC(tq2);
-                if (VEC && LC_RES_PLANAR_LM) {
+                if (VEC && kind != CTL_EVAL_COST && (a.flags & LC_FLAG_LM_MIXED)) {
+                    if (wgen) lm_eval_pass_mixed<NT, true>(a, s, l, b, n, sanitize);
+                    else lm_eval_pass_mixed<NT, false>(a, s, l, b, n, sanitize);
+                } else if (VEC && LC_RES_PLANAR_LM) {
                     if (kind == CTL_EVAL_COST) {
                         if (wgen) lm_eval_pass_planar<NT, false, true>(a, s, l, b, n, sanitize);
                         else lm_eval_pass_planar<NT, false, false>(a, s, l, b, n, sanitize);

@@ -461,6 +461,87 @@ __device__ __forceinline__ void lm_eval_accum_planar(const lc_args& a, const Pos
     acc[27] *= 0.5;
 }
 
+// Mixed-precision Jacobian pass (LC_FLAG_LM_MIXED).  fp64: q = R X, p, 1/z, the projection, the residual and the cost, exactly
+// as in lm_eval_accum_planar (every trust-region decision keeps its fp64 inputs).  fp32: the two Jacobian rows, stored as
+// pairs (J0_i, J1_i), and their sums — J'^T J' as 21 FFMA2 whose two lanes are the two rows (added in fp64 at the end), J'^T r
+// as 6 FFMA2.  Per point: 29 fp64 operations instead of 103; the per-thread fp32 partial sums (<= N/NT points) are reduced
+// across the CTA in fp64.
+template <int NT, bool WGEN>
+__device__ __forceinline__ void lm_eval_accum_mixed(const lc_args& a, const PoseShared& s, const ResLayout& l, int b, int n, bool sanitize, int tid,
+                                                    double (&acc)[28]) {
+    const LmState& L = s.lm;
+    float2 A2[kSym], g2[6];
+#pragma unroll
+    for (int k = 0; k < kSym; ++k) A2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g2[k] = make_float2(0.f, 0.f);
+    double cost = 0.0;
+    const double k00 = s.K[0], k01 = s.K[1], k10 = s.K[3], k11 = s.K[4];
+    const float kf00 = static_cast<float>(k00), kf01 = static_cast<float>(k01), kf10 = static_cast<float>(k10), kf11 = static_cast<float>(k11);
+    const double R0 = L.Rm[0], R1 = L.Rm[1], R2 = L.Rm[2], R3 = L.Rm[3], R4 = L.Rm[4], R5 = L.Rm[5], R6 = L.Rm[6], R7 = L.Rm[7], R8 = L.Rm[8];
+    const double t0 = L.te[0], t1 = L.te[1], t2 = L.te[2];
+    const volatile double* Kv = s.K;   // cx, cy are re-read from shared memory where used
+    const float* w0p = static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0];
+    const float* w1p = w0p + a.weights.stride[2];
+    const bool icov = WGEN && a.weight_mode == LC_W_ICOV_DIAG;
+    float wn0 = 0.f, wn1 = 0.f;
+    if (tid < n) { wn0 = __ldg(w0p + tid); wn1 = __ldg(w1p + tid); }
+    for (int i = tid; i < n; i += NT) {
+        float wa = wn0, wb = wn1;
+        const int inext = i + NT;
+        if (inext < n) { wn0 = __ldg(w0p + inext); wn1 = __ldg(w1p + inext); }
+        if (WGEN) {
+            if (sanitize) { wa = nan_to_num_f(wa); wb = nan_to_num_f(wb); }
+            if (icov) { wa = sqrtf(wa); wb = sqrtf(wb); }
+        }
+        const float laf = fabsf(wa), lcf = fabsf(wb);
+        const double X0 = l.A0[i], X1 = l.A1[i], X2 = l.A2[i];
+        const double px = l.B0[i], py = l.B1[i];
+        const double q0 = fma(R0, X0, fma(R1, X1, R2 * X2));
+        const double q1 = fma(R3, X0, fma(R4, X1, R5 * X2));
+        const double q2 = fma(R6, X0, fma(R7, X1, R8 * X2));
+        const double p0 = q0 + t0, p1 = q1 + t1, p2 = q2 + t2;
+        const double iz = fast_rcp(p2);
+        const double up = fma(p0, k00, p1 * k01) * iz, vp = fma(p0, k10, p1 * k11) * iz;
+        const double du = up - (px - Kv[2]), dv = vp - (py - Kv[5]);
+        const double r0 = du * static_cast<double>(laf), r1 = dv * static_cast<double>(lcf);
+        cost = fma(r0, r0, fma(r1, r1, cost));
+        // ---- fp32 from here: Jacobian rows in the left basis, J'_c = [q x D_c | D_c] ----
+        const float qf0 = static_cast<float>(q0), qf1 = static_cast<float>(q1), qf2 = static_cast<float>(q2);
+        const float izf = static_cast<float>(iz), upf = static_cast<float>(up), vpf = static_cast<float>(vp);
+        const float2 rr = make_float2(static_cast<float>(r0), static_cast<float>(r1));
+        const float a0 = laf * izf, a1 = lcf * izf;
+        float2 P[6];   // (row 0, row 1) of column i
+        P[3] = make_float2(a0 * kf00, a1 * kf10);
+        P[4] = make_float2(a0 * kf01, a1 * kf11);
+        P[5] = make_float2(-a0 * upf, -a1 * vpf);
+        const float2 Q0 = make_float2(qf0, qf0), Q1 = make_float2(qf1, qf1), Q2 = make_float2(qf2, qf2);
+        const float2 nQ0 = make_float2(-qf0, -qf0), nQ1 = make_float2(-qf1, -qf1), nQ2 = make_float2(-qf2, -qf2);
+        P[0] = __ffma2_rn(Q1, P[5], __fmul2_rn(nQ2, P[4]));
+        P[1] = __ffma2_rn(Q2, P[3], __fmul2_rn(nQ0, P[5]));
+        P[2] = __ffma2_rn(Q0, P[4], __fmul2_rn(nQ1, P[3]));
+        int k2 = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int cc = r; cc < 6; ++cc) { A2[k2] = __ffma2_rn(P[r], P[cc], A2[k2]); ++k2; }
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) g2[cc] = __ffma2_rn(P[cc], rr, g2[cc]);
+    }
+#pragma unroll
+    for (int k = 0; k < kSym; ++k) acc[k] = static_cast<double>(A2[k].x) + static_cast<double>(A2[k].y);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[21 + k] = static_cast<double>(g2[k].x) + static_cast<double>(g2[k].y);
+    acc[27] = 0.5 * cost;
+}
+
+template <int NT, bool WGEN>
+__device__ __forceinline__ void lm_eval_pass_mixed(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
+    double acc[28];
+    lm_eval_accum_mixed<NT, WGEN>(a, s, l, b, n, sanitize, threadIdx.x, acc);
+    block_reduce<28, NT>(acc, s.red, s.fin);
+}
+
 template <int NT, bool JAC, bool WGEN>
 __device__ __forceinline__ void lm_eval_pass_planar(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
     double acc[28];

@@ -18,10 +18,14 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
                    bbox_3d: Tensor, *, max_iter_count=50, function_tolerance=1e-6, max_err_len=32.0, rel_thresh=3.0,
                    w_e_thresh=4.0, need=(True, False, True), grad_out: Optional[Tensor] = None, grad_scale=1.0,
                    tol_needs_success=True, out: Optional[dict] = None, force_streaming=False,
-                   loss_sum: Optional[Tensor] = None):
+                   loss_sum: Optional[Tensor] = None, mixed: bool = True):
     """Returns dict(states, radius, invalid, iters, loss, g_pts3d, g_pts2d, g_inv_std, flags).
 
     ``out`` may carry preallocated output tensors from a previous call (same shapes) to avoid allocation.
+    ``mixed`` (default on) lets the resident kernels form the Jacobian sums of the solve in packed fp32 (``LC_FLAG_LM_MIXED``):
+    residuals, cost and every trust-region decision stay fp64; over 10 240 poses the iteration counts, accept / reject sequences
+    and invalid flags are identical to the all-fp64 pass and the poses agree to one fp32 ulp (``profiles/lm_mixed_check_r2.md``).
+    ``cer_solver.solve`` / ``lm_solve`` keep the all-fp64 pass by default.
     """
     dev = nat.check_cuda(K, start, pts3d, pts2d, inv_std, valid, bbox_3d, grad_out)
     dt = pts3d.dtype
@@ -38,7 +42,8 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
                g_pts3d=dense_like("g_pts3d", pts3d) if need[0] else None,
                g_pts2d=dense_like("g_pts2d", pts2d.expand(B, N, 2)) if need[1] else None,
                g_inv_std=dense_like("g_inv_std", inv_std) if need[2] else None)
-    flags = (nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0) | (nat.FLAG_FORCE_STREAMING if force_streaming else 0)
+    flags = ((nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0) | (nat.FLAG_FORCE_STREAMING if force_streaming else 0)
+             | (nat.FLAG_LM_MIXED if mixed else 0))
     ftol = nat.as_c_float(function_tolerance)
     fit = nat.fit
     args = nat.make_args(B, N, dt, K=fit(K, (B, 3, 3), dt), pose=fit(start, (B, 7), dt), pts3d=pts3d,

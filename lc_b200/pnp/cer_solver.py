@@ -39,7 +39,7 @@ def _batch_tensors(*tensor_lsts, device=None):
 def lm_solve(cam_mat: Tensor, pts3d: Tensor, pts2d: Tensor, weights: Tensor, start: Tensor,
              n_points: Optional[Tensor] = None, *, weight_mode: int = nat.W_ICOV_DIAG, max_iter_count: int = 50,
              function_tolerance: float = 1e-6, filter_input_nan: bool = False, tol_needs_success: bool = True,
-             want_trace: bool = False, force_streaming: bool = False):
+             want_trace: bool = False, force_streaming: bool = False, mixed: bool = False):
     """Batched kernel call.  Returns dict(states, radius, invalid (int32), iters[, trace])."""
     dev = nat.check_cuda(cam_mat, pts3d, pts2d, weights, start, n_points)
     dt = pts3d.dtype
@@ -50,7 +50,7 @@ def lm_solve(cam_mat: Tensor, pts3d: Tensor, pts2d: Tensor, weights: Tensor, sta
     iters = torch.empty(B, dtype=torch.int32, device=dev)
     trace = torch.full((B, max_iter_count + 2, 4), float("nan"), dtype=torch.float64, device=dev) if want_trace else None
     flags = ((nat.FLAG_NAN_TO_NUM if filter_input_nan else 0) | (nat.FLAG_TOL_NEEDS_SUCCESS if tol_needs_success else 0)
-             | (nat.FLAG_FORCE_STREAMING if force_streaming else 0))
+             | (nat.FLAG_FORCE_STREAMING if force_streaming else 0) | (nat.FLAG_LM_MIXED if mixed else 0))
     # the reference ABI carries function_tolerance as a C float (ext.h:10)
     ftol = nat.as_c_float(function_tolerance)
     npts = None if n_points is None else n_points.to(device=dev, dtype=torch.int32).contiguous()

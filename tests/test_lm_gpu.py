@@ -123,3 +123,26 @@ def test_headline_size_lm_is_a_fixed_point_and_batch_independent():
     r = lm_solve(c.K, c.pts3d, c.pts2d, c.inv_std, o["states"], weight_mode=nat.W_INV_STD)
     ang = quat_angle(r["states"][:, :4].cpu().double().numpy(), o["states"][:, :4].cpu().double().numpy())
     assert (r["invalid"] == 0).all() and ang.max() < 5e-4 and int(r["iters"].max()) <= 3   # the early-stop gap
+
+
+def test_mixed_precision_pass_keeps_the_schedule(oracle):
+    """LC_FLAG_LM_MIXED (resident kernels, planar fp32 weights): Jacobian sums in packed fp32, everything that decides in fp64.
+    Same iteration counts / accept flags / invalid flags as the oracle and the all-fp64 pass, poses within the north-star
+    tolerance; the trace's costs agree to 1e-5 (the iterates differ by ~1e-6 of a step)."""
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200 import _native as nat
+    c = make_correspondences(24, 2048, 41).to(torch.float32)
+    ref = oracle.lm_solve(c.K, c.pts3d, c.pts2d, torch.diag_embed((c.inv_std ** 2).sqrt()), c.start, want_trace=True)
+    d = c.to(device="cuda")
+    X, x, w = planar_view(d.pts3d), planar_view(d.pts2d), planar_view(d.inv_std)
+    o = lm_solve(d.K, X, x, w, d.start, weight_mode=nat.W_INV_STD, want_trace=True, mixed=True)
+    assert b"vec4" in nat.lib().lc_b200_last_kernels()
+    f = lm_solve(d.K, X, x, w, d.start, weight_mode=nat.W_INV_STD, want_trace=True)
+    assert np.array_equal(o["iters"].cpu().numpy(), ref["iters"]) and np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"])
+    assert torch.equal(o["iters"], f["iters"])
+    _check_states(o["states"].cpu().numpy(), ref["states"].astype(np.float64))
+    tg, tr = o["trace"].cpu().numpy(), ref["trace"]
+    m = ~np.isnan(tr)
+    assert np.array_equal(np.isnan(tg), np.isnan(tr))
+    assert np.array_equal(tg[m].reshape(-1, 4)[:, 2], tr[m].reshape(-1, 4)[:, 2])            # accept / reject sequence
+    assert np.allclose(tg[m].reshape(-1, 4)[:, :2], tr[m].reshape(-1, 4)[:, :2], rtol=1e-5)  # cost, radius
