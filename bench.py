@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--points", type=int, default=N_PTS)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch poses PER GPU (default); strong: --batch poses in total, split over the ranks")
+    ap.add_argument("--lm-mixed", action="store_true", help="LC_FLAG_LM_MIXED: Jacobian sums of the solve in packed fp32 (opt-in experiment)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -244,7 +245,7 @@ def main():
     per = "/GPU" if a.scaling == "weak" else f" in total ({a.batch}/GPU)"
     workload = f"isolated LC op {a.pipeline}: B={a.batch * (world if a.scaling == 'strong' else 1)}{per} x N={a.points} dense correspondences (BASELINE.json configs[1])"
     rot_mb = a.batch * a.points * 28 / 1e6
-    config = {"workload": workload, "pipeline": a.pipeline, "batch_per_gpu": a.batch, "points": a.points,
+    config = {"workload": workload, "pipeline": a.pipeline, "lm_mixed": bool(a.lm_mixed), "batch_per_gpu": a.batch, "points": a.points,
               "parallelism": f"batch-sharded x{world}",
               "l2": f"inputs rotate over {N_ROTATE} distinct resident batches ({N_ROTATE}x{rot_mb:.0f} MB) > 126 MB L2"}
 
@@ -329,11 +330,12 @@ def main():
             acc = sums[k]
             acc.zero_()
         if a.pipeline == "p3":
-            r = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, out=out, loss_sum=acc)
+            r = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, out=out, loss_sum=acc,
+                               mixed=a.lm_mixed)
         elif a.pipeline == "p1":
             r = loss_fwd_bwd(d["K"], d["pose"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go, loss_sum=acc)
         else:
-            r = lm_solve(d["K"], p3, p2, s, d["start"], weight_mode=nat.W_INV_STD)
+            r = lm_solve(d["K"], p3, p2, s, d["start"], weight_mode=nat.W_INV_STD, mixed=a.lm_mixed)
         # what the library actually dispatched for this call (lc_abi.cu: every launch site records itself)
         observed["launches"] += handle.lc_b200_last_launch_count()
         observed["kernels"].add(handle.lc_b200_last_kernels().decode())
@@ -373,26 +375,23 @@ def main():
     barrier()
     launches_timed = observed["launches"]
     ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
     n_in_region = len(sampler.samples) if rank == 0 else 0
-    if rank == 0 and n_in_region < 20:
-        # the timed region was shorter than a few NVML polls: keep the SAME step running (untimed) until the sampler has seen
-        # the clocks under this load for ~0.3 s
-        t_end = time.perf_counter() + 0.3
-        i = 0
-        while time.perf_counter() < t_end:
+    if ms < 300.0:
+        # the timed region is shorter than a few NVML polls: keep the SAME step running (untimed, the same number of steps on every
+        # rank: the step contains the ranks' all-reduce) until the sampler has seen the clocks under this load for ~0.3 s
+        for i in range(min(4000, int(300.0 / max(ms / a.steps, 1e-3)) + 1)):
             step(devb[i % n_rot], outs)
-            i += 1
-            if i % 16 == 0:
+            if i % 16 == 15:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["samples_in_timed_region"] = n_in_region
     barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * a.steps / (ms * 1e-3)
 
     # ---- end to end: host buffers in, the whole result out (loss, states, gradients), three streams ----

@@ -65,7 +65,7 @@ enum {
                                       in fp64 as always, but the Jacobian rows and their sums J^T J, J^T r in packed fp32 per thread (fp64
                                       across threads).  Moves ~3/4 of the pass off the fp64 pipe.  The iterates differ from the all-fp64
                                       pass by ~1e-6 of a step (<< the 1e-6 rad tolerance); profiles/lm_mixed_check_r2.md holds the
-                                      iteration-count / accept-flag comparison over 10k poses.  Ignored by the other kernels. */
+                                      iteration-count / accept-flag comparison over 10k poses.  Opt-in; ignored by the other kernels. */
 };
 
 /* per-pose status bits written to `lc_flags` */

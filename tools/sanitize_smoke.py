@@ -9,8 +9,13 @@ from lc_b200.pnp.cer_solver import lm_solve
 from lc_b200.nll.pnp_auto import weighted_pnp_jac_wrt_pts2d
 from lc_b200 import _native as nat
 
-for (B, N) in [(3, 8), (2, 70), (2, 700), (2, 1300), (2, 2500)]:   # 2500: tensor-memory variant of the loss kernel
+for (B, N) in [(3, 8), (2, 70), (2, 700), (2, 1300), (2, 2500)]:   # 8: thread-per-pose kernel; 2500: tensor-memory variant of the loss kernel
     c = make_correspondences(B, N, 1).to(torch.float32).to(device="cuda")
+    if N % 4 == 0:   # planar slabs: vectorised point loops, TMA-out gradients, mixed-precision LM pass
+        X, x, w = planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std)
+        loss_fwd_bwd(c.K, c.pose, X, x, w, c.valid, c.bbox_3d, want_cov=True)
+        solve_and_loss(c.K, c.start, X, x, w, None, c.bbox_3d, need=(True, True, True))
+        lm_solve(c.K, X, x, w, c.start, weight_mode=nat.W_INV_STD, n_points=torch.tensor([N, N - 3][:B] + [N] * (B - 2), dtype=torch.int32, device="cuda"))
     for stream in (False, True):
         loss_fwd_bwd(c.K, c.pose, planar_view(c.pts3d), c.pts2d, planar_view(c.inv_std), c.valid, c.bbox_3d, want_cov=True, force_streaming=stream)
         solve_and_loss(c.K, c.start, c.pts3d, c.pts2d, c.inv_std, None, c.bbox_3d, need=(True, True, True), force_streaming=stream)
@@ -49,5 +54,14 @@ c32 = c.to(torch.float32).to(device="cuda")
 candi = torch.cat((Rg.float(), c32.pose[:, 4:, None]), -1)[:, None].repeat(1, 5, 1, 1)
 select_pose_2d(c32.K, c32.pts3d, c32.pts2d, candi)
 select_pose_3d(c32.K, c32.pts3d, (c32.pts3d @ Rg.float().mT + c32.pose[:, None, 4:]) @ c32.K.mT, candi)
+# the opt-in persistent kernel (one CTA per SM, two poses in flight) and the reference-ABI entry point with host pointer tables
+os.environ["LC_B200_PERSIST"] = "1"
+c = make_correspondences(150, 2048, 3).to(torch.float32).to(device="cuda")
+X, x, w = planar_view(c.pts3d), planar_view(c.pts2d), planar_view(c.inv_std)
+loss_fwd_bwd(c.K, c.pose, X, x, w, None, c.bbox_3d)
+solve_and_loss(c.K, c.start, X, x, w, None, c.bbox_3d, need=(True, True, True))
+lm_solve(c.K, X, x, w, c.start, weight_mode=nat.W_INV_STD)
+assert b"persist" in nat.lib().lc_b200_last_kernels()
+del os.environ["LC_B200_PERSIST"]
 torch.cuda.synchronize()
 print("sanitize smoke done")

@@ -136,7 +136,7 @@ def main():
         model.loss_fn = losses.Loss_fn(cfg.loss, cfg, total_bits).to(dev)
         net = model
         if a.ddp and world > 1:
-            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
         opt = torch.optim.Adam(model.parameters(), lr=cfg.optimizer.lr, weight_decay=cfg.optimizer.wd)   # Ranger for glmo in the reference; Adam here for both
         return model, net, opt
 
@@ -149,7 +149,7 @@ def main():
             probe["out_grads"] = {}
             for k, v in out.items():
                 if v.requires_grad:
-                    v.register_hook(lambda g, k=k: probe["out_grads"].__setitem__(k, g.detach().clone()))
+                    v.register_hook(lambda g, k=k: probe["out_grads"].__setitem__(k, g.detach().clone()) if g is not None else None)
         loss_dict, w = model.loss_fn(gt, out, EPOCH, STEP, SPE)
         loss = sum(w.values())
         opt.zero_grad(set_to_none=True)
