@@ -26,14 +26,17 @@ def _as_batched(t: Tensor, tail: int):
 def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std: Tensor, valid: Optional[Tensor],
                  bbox_3d: Tensor, *, max_err_len=32.0, rel_thresh=3.0, w_e_thresh=4.0, need=(True, True, True),
                  grad_out: Optional[Tensor] = None, grad_scale: float = 1.0, want_cov=False,
-                 force_streaming=False, loss_sum: Optional[Tensor] = None):
+                 force_streaming=False, loss_sum: Optional[Tensor] = None, n_points: Optional[Tensor] = None):
     """One launch: per-pose loss and d loss/d (pts3d, pts2d, inv_std) scaled by grad_scale*grad_out[b].
+
+    ``n_points`` (B,) int32: ragged batch padded to N, only the first n_points[b] correspondences of pose b count (the padding
+    gets zero gradients), like ``lm_solve``.
 
     All tensors batched: K (B,3,3), pose (B,7), pts3d (B,N,3), pts2d (B,N,2), inv_std (B,N,2),
     valid (B,N)|None, bbox_3d (B,8,3); any strides.  Returns dict(loss, g_pts3d, g_pts2d, g_inv_std,
     flags[, cov, update_cov]); gradients not requested in ``need`` are None.
     """
-    dev = nat.check_cuda(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, grad_out)
+    dev = nat.check_cuda(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, grad_out, n_points)
     dt = pts3d.dtype
     B, N = pts3d.shape[0], pts3d.shape[1]
     fit = nat.fit
@@ -52,7 +55,7 @@ def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std:
                          bbox=bbox_3d, grad_out=grad_out, loss=loss, g_pts3d=g3, g_pts2d=g2, g_weights=gs,
                          cov=cov, update_cov=ucov, lc_flags=flags, max_err_len=float(max_err_len),
                          rel_thresh=float(rel_thresh), w_e_thresh=float(w_e_thresh), grad_scale=float(grad_scale),
-                         flags=nat.FLAG_FORCE_STREAMING if force_streaming else 0, loss_sum=loss_sum)
+                         flags=nat.FLAG_FORCE_STREAMING if force_streaming else 0, loss_sum=loss_sum, n_points=n_points)
     nat.call("lc_b200_loss_fwd_bwd", args, dev)
     out = dict(loss=loss, g_pts3d=g3, g_pts2d=g2, g_inv_std=gs, flags=flags)
     if want_cov:

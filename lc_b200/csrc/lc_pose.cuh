@@ -341,8 +341,9 @@ __device__ inline void angle_axis_to_quat(const double* aa, double* q) {
 
 // LM epilogue (thread 0): ceres.cpp:134-144 writes the state back only when valid; cer_solver.py:51-52 keeps
 // `start` otherwise.  s.pose becomes the pose the LC phase runs at (rounded to the I/O type like the reference).
+// `leader` = false: a non-leading CTA of a cluster-split pose (lc_resident_kernel.cuh) only updates its copy of the pose.
 template <typename T, class PS = PoseShared>
-__device__ inline void lm_write_result(const lc_args& a, PS& s, int b, int n, bool solved) {
+__device__ inline void lm_write_result(const lc_args& a, PS& s, int b, int n, bool solved, bool leader = true) {
     LmState& L = s.lm;
     if (solved) {
         double q[4];
@@ -350,6 +351,7 @@ __device__ inline void lm_write_result(const lc_args& a, PS& s, int b, int n, bo
         for (int k = 0; k < 4; ++k) s.pose[k] = static_cast<double>(static_cast<T>(q[k]));
         for (int k = 0; k < 3; ++k) s.pose[4 + k] = static_cast<double>(static_cast<T>(L.x[3 + k]));
     }
+    if (!leader) return;
     if (a.state.ptr)
         for (int k = 0; k < 7; ++k) st<T>(a.state, b * a.state.stride[0] + k * a.state.stride[1], s.pose[k]);
     if (a.radius.ptr) st<T>(a.radius, b * a.radius.stride[0], n >= 3 ? L.reported_radius : 1.0);
@@ -846,8 +848,9 @@ __device__ __forceinline__ void lc_pose_setup_warp(PoseShared& s, bool decouple_
 
 // Called by one warp (all 32 lanes converged).  In: s.fin[0..48) = H', G' (packed), b'; s.rows.  Writes the loss / flags /
 // optional covariances and, when want_grads, s.cHL, s.cGL, s.bL.  The caller follows with a barrier.
+// `leader` = false (non-leading CTA of a cluster-split pose): same computation, no per-pose outputs written.
 template <typename T, bool WITH_COV = true>
-__device__ __forceinline__ void lc_six_fast(const lc_args& a, PoseShared& s, int b, bool want_grads) {
+__device__ __forceinline__ void lc_six_fast(const lc_args& a, PoseShared& s, int b, bool want_grads, bool leader = true) {
     const int lane = threadIdx.x & 31;
     int r = 0, c = 0;
     if (lane < kSym) sym_rc(lane, r, c);
@@ -949,7 +952,7 @@ __device__ __forceinline__ void lc_six_fast(const lc_args& a, PoseShared& s, int
     const double go = a.grad_scale * (a.grad_out.ptr ? ld<T>(a.grad_out, b * a.grad_out.stride[0]) : 1.0);
     const double g_p = go * (ip - 0.5 * (cov_err + lin) * ip * ip);
     const double g_c = go * 0.5 * ip;
-    if (lane == 0) {
+    if (lane == 0 && leader) {
         const double loss = log(prior) + 0.5 * (cov_err + lin) * ip;
         if (a.loss.ptr) st<T>(a.loss, b * a.loss.stride[0], loss);
         if (a.lc_flags) a.lc_flags[b] = s.flag;
@@ -959,7 +962,7 @@ __device__ __forceinline__ void lc_six_fast(const lc_args& a, PoseShared& s, int
     const double wq = gq == 0 ? (goodC ? g_p * 0.0625 * rs : 0.0) : (gq == 1 ? (goodM ? g_c * 0.0625 * rs : 0.0) : g_c * 0.125 * rs);
     const int jc = (lane < 24 ? lane : 0) / 3;
     const double wC = __shfl_sync(kFull, wq, jc), wM = __shfl_sync(kFull, wq, 8 + jc), wU = __shfl_sync(kFull, wq, 16 + jc);
-    if (WITH_COV && (a.cov.ptr || a.update_cov.ptr)) {
+    if (WITH_COV && leader && (a.cov.ptr || a.update_cov.ptr)) {
         // reference-basis covariances on request: S_ref = Tm^-1 S' Tm^-T with M' = C' G' C' formed explicitly (not on the training path)
         for (int e = lane; e < 36; e += 32) s.G[e] = s.fin[21 + sym_at(e / 6, e % 6)];
         __syncwarp();

@@ -97,8 +97,42 @@ static bool vec_ok(const lc_args& a, int mode) {
     return true;
 }
 
-int launch_res_scalar(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, int cap, int max_smem, int tma_mask) {
-    return launch_res_any<false>(a, mode, nt, tm, st, cap, max_smem, tma_mask);
+int launch_res_scalar(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, const ResLaunch& r) {
+    return launch_res_any<false, 1>(a, mode, nt, tm, st, r);
+}
+
+static std::atomic<int> g_num_sms[64];
+static int num_sms() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const bool cached = dev >= 0 && dev < 64;
+    if (cached && (v = g_num_sms[dev].load(std::memory_order_relaxed)) > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cached) g_num_sms[dev].store(v, std::memory_order_relaxed);
+    return v;
+}
+
+// Poses split over two-CTA clusters (lc_resident_kernel.cuh, CL = 2).  Measured on B200 at N = 4096 (profiles/README.md, "cluster
+// split"): a CTA that has an SM to itself already runs a pose in 0.72x the time it takes next to a second CTA, and halving its
+// points only shortens the point passes (the serial trust-region / 6x6 sections, the reductions and a cluster barrier per
+// reduction stay), so
+//   * B <= SMs / 2 (every half-pose CTA gets its own SM): P3 74 -> 67 us.  This is the default use;
+//   * splitting the poses of the last, partly empty wave of a larger launch (B = 1024 on 296 slots: 136 poses as 272 half-pose
+//     CTAs in front of 888 = 3 full waves) LOSES: 345 -> 390 us, because those 136 CTAs, alone on their SMs, take 76 us either way
+//     and the second launch adds its ramp-up.  Kept reachable for A/B runs: LC_B200_SPLIT = 1 splits whenever the last wave fills
+//     at most half of the slots, LC_B200_SPLIT = 0 never splits; LC_B200_PDL = 0 turns off the programmatic launch of the main
+//     grid behind the cluster grid.
+static int split_tail(const lc_args& a, int nt, bool vec, bool tm, int cap) {
+    if (!vec || tm || cap != 0 || a.N < 512) return 0;
+    const char* e = getenv("LC_B200_SPLIT");
+    if (e && e[0] == '0') return 0;
+    const int sms = num_sms();
+    if (sms <= 0) return 0;
+    if (!(e && e[0] == '1')) return (2 * a.B <= sms && a.N >= 2048) ? a.B : 0;
+    const int slots = (nt <= 128 ? 4 : 2) * sms;
+    if (a.B / slots > 8) return 0;   // many waves: the tail no longer matters
+    const int tail = a.B % slots;
+    return (tail > 0 && 2 * tail <= slots) ? tail : 0;
 }
 
 // cap > 0: ragged batch whose padded N exceeds the resident limit; only poses with n_points <= cap are processed here
@@ -111,8 +145,19 @@ int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st, int cap) {
     int nt = tm ? 128 : resident_threads_for(cap > 0 ? cap : a.N, mode);
     if (nt != 128 && nt != 192 && nt != 256) nt = 256;
     if (nt == 192 && mode != MODE_LM) nt = 256;
-    const int max_smem = max_optin_smem(), tma_mask = tma_mask_for(a);
-    return vec ? launch_res_vec(a, mode, nt, tm, st, cap, max_smem, tma_mask) : launch_res_scalar(a, mode, nt, tm, st, cap, max_smem, tma_mask);
+    ResLaunch r{cap, max_optin_smem(), tma_mask_for(a), 0, a.B, 1, 0};
+    const int tail = split_tail(a, nt, vec, tm, cap);
+    if (tail > 0) {
+        const char* e = getenv("LC_B200_PDL");
+        const bool pdl = !(e && e[0] == '0') && tail < a.B;
+        ResLaunch rc = r;
+        rc.pose_base = a.B - tail; rc.count = tail; rc.cl = 2; rc.pdl = pdl ? 1 : 0;
+        const int rcode = launch_res_cluster2(a, mode, nt, st, rc);
+        if (rcode != 0 || tail == a.B) return rcode;
+        r.count = a.B - tail;
+        r.pdl |= pdl ? 2 : 0;
+    }
+    return vec ? launch_res_vec(a, mode, nt, tm, st, r) : launch_res_scalar(a, mode, nt, tm, st, r);
 }
 
 // Ragged batches (n_points given) whose padded N does not fit: the poses with n_points <= cap still can take the resident

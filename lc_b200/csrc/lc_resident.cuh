@@ -47,7 +47,7 @@ inline size_t resident_smem_bytes_tm(int n) {
     return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * 2 * static_cast<size_t>(round_up4(n));
 }
 
-inline size_t resident_smem_bytes(int n) {
+__host__ __device__ inline size_t resident_smem_bytes(int n) {
     return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * 5 * static_cast<size_t>(round_up4(n));
 }
 
@@ -136,10 +136,59 @@ struct XAcc {
 #define LC_POINT_LOOP(TM, NT, n)                                                                                   \
     for (int i = threadIdx.x, k = 0; ((TM) ? (k * (NT) + static_cast<int>(threadIdx.x & ~31u)) : i) < (n); i += (NT), ++k)
 
+// ---- one pose split over a thread-block cluster (lc_resident_kernel.cuh, CL > 1) ----
+// The CTAs of a cluster each hold a contiguous share of the pose's points and run the SAME code on it; after every CTA-wide
+// reduction the per-CTA totals are exchanged through distributed shared memory and summed in rank order, so every CTA of the
+// cluster continues with bit-identical totals and takes identical decisions in the (redundantly executed) serial sections.
+// One cluster barrier per reduction: the exchange buffer alternates, a CTA cannot be two reductions ahead of a peer.
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_smem, unsigned rank) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem)), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
+struct ClusterShared {
+    lc_args args;        // this CTA's view of the call: point-indexed pointers advanced to its share, N = its share
+    double xch[2][48];   // reduction exchange, double-buffered
+};
+template <int CL>
+struct Clu {
+    double (*xch)[48];
+    int parity, n_total;   // n_total: points of the whole pose (statistics that divide by the count)
+    bool leader;           // rank 0 writes the per-pose outputs
+    template <int V>
+    __device__ __forceinline__ void combine(double* fin) {   // after block_reduce: fin[0..V) := sum over the cluster's CTAs
+        const int tid = threadIdx.x;
+        double* mine = xch[parity];
+        if (tid < V) mine[tid] = fin[tid];
+        cluster_sync_all();
+        if (tid < V) {
+            double t = 0.0;
+#pragma unroll
+            for (unsigned r = 0; r < CL; ++r) t += ld_dsmem_f64(mine + tid, r);
+            fin[tid] = t;
+        }
+        __syncthreads();
+        parity ^= 1;
+    }
+};
+template <>
+struct Clu<1> {
+    int n_total;
+    static constexpr bool leader = true;
+    template <int V>
+    __device__ __forceinline__ void combine(double*) {}
+};
+
 // One evaluation pass of the reprojection cost (ceres.cpp:30-55) at the point held in L.Rm/L.te, from the
 // staged fp32 arrays: cost, and when JAC also J'^T J' and J'^T r in the left basis.
-template <int NT, bool JAC, bool TM>
-__device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize, const XAcc<TM>& xs) {
+template <int NT, bool JAC, bool TM, class CLU>
+__device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize, const XAcc<TM>& xs, CLU& cl) {
     const LmState& L = s.lm;
     double acc[28];
 #pragma unroll
@@ -200,6 +249,7 @@ __device__ __forceinline__ void lm_eval_pass_res(const lc_args& a, PoseShared& s
     }
     acc[27] *= 0.5;
     block_reduce<28, NT>(acc, s.red, s.fin);
+    cl.template combine<28>(s.fin);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -19,16 +19,54 @@ namespace lc {
 __device__ int g_live_ctas[256];   // CTAs currently resident per SM (tools/phase_timing.py: measured concurrency)
 #endif
 
-template <int NT, int MODE, bool TM, bool VEC>
-__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a, int npad, int tma_mask, int n_max) {
+template <int CL>
+__device__ __forceinline__ const lc_args& pick_args(const lc_args& param, const lc_args& shared) {
+    if constexpr (CL == 1) return param;
+    else return shared;
+}
+
+// CL > 1: one pose per thread-block CLUSTER of CL CTAs (launched with cudaLaunchAttributeClusterDimension); CTA `rank` holds the
+// points [rank * npad, rank * npad + npad) and sees them through its own copy of the arguments (ClusterShared::args) whose
+// point-indexed pointers are advanced to its share, so every point loop below runs unchanged on the share.  The reductions are
+// completed across the cluster (Clu::combine), the serial sections run redundantly in every CTA, rank 0 writes the per-pose outputs.
+// Used for the poses of a launch that would otherwise leave most CTA slots of the last wave empty (lc_resident.cu).
+// pdl: bit 0 = let the next kernel of the stream start as soon as this grid's CTAs are resident (griddepcontrol.launch_dependents),
+// bit 1 = this grid was launched that way behind another one: wait for it before exiting (stream order of completion).
+template <int NT, int MODE, bool TM, bool VEC, int CL>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(const lc_args a_in, int npad, int tma_mask, int n_max, int pose_base, int pdl) {
     static_assert(!(TM && VEC), "the vectorised phase keeps the model points in shared memory");
+    static_assert(CL == 1 || (VEC && !TM), "cluster-split poses use the vectorised shared-memory kernel");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
     const ResLayout l = TM ? res_layout_tm(smem_raw, npad) : res_layout(smem_raw, npad);
-    const int b = blockIdx.x;
+    const int b = pose_base + static_cast<int>(blockIdx.x) / CL;
     const int tid = threadIdx.x;
-    const int n = a.n_points ? min(max(a.n_points[b], 0), a.N) : a.N;
-    if (n > n_max) return;   // ragged batch split by n_points: this pose belongs to the streaming launch (lc_abi.cu)
+    if (pdl & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int n_total = a_in.n_points ? min(max(a_in.n_points[b], 0), a_in.N) : a_in.N;
+    if (CL == 1 && n_total > n_max) return;   // ragged batch split by n_points: this pose belongs to the streaming launch (lc_abi.cu)
+    ClusterShared& cs = *reinterpret_cast<ClusterShared*>(smem_raw + resident_smem_bytes(CL > 1 ? npad : 0));
+    Clu<CL> cl;
+    cl.n_total = n_total;
+    int n = n_total;
+    if constexpr (CL > 1) {
+        const int rank = static_cast<int>(cluster_ctarank());
+        const int off = rank * npad;
+        if (tid == 0) {
+            cs.args = a_in;
+            lc_args& A = cs.args;
+            A.N = min(max(a_in.N - off, 0), npad);
+            auto adv = [&](lc_view& v) { if (v.ptr) v.ptr = static_cast<float*>(v.ptr) + off * v.stride[1]; };
+            adv(A.pts3d); adv(A.pts2d); adv(A.weights); adv(A.valid); adv(A.g_pts3d); adv(A.g_pts2d); adv(A.g_weights);
+        }
+        __syncthreads();
+        n = min(max(n_total - off, 0), npad);
+        cl.xch = cs.xch; cl.parity = 0; cl.leader = rank == 0;
+    }
+    const lc_args& a = pick_args<CL>(a_in, cs.args);
+    auto finish = [&]() {
+        if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still read its exchange buffer
+        if (pdl & 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+    };
     const bool sanitize = (MODE & MODE_LM) && (a.flags & LC_FLAG_NAN_TO_NUM);
     uint32_t tb = 0;
     if (TM) {
@@ -158,10 +196,10 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
 #ifdef LC_TIMING
         double* trace = nullptr;
 #else
-        double* trace = a.trace ? a.trace + (int64_t)b * (a.max_iter + 2) * 4 : nullptr;
+        double* trace = (a.trace && cl.leader) ? a.trace + (int64_t)b * (a.max_iter + 2) * 4 : nullptr;
 #endif
         bool solved = false;
-        if (n >= 3) {
+        if (n_total >= 3) {
             if (tid == 0) {
                 quat_to_angle_axis(s.pose, L.x);
                 L.x[3] = s.pose[4]; L.x[4] = s.pose[5]; L.x[5] = s.pose[6];
@@ -174,18 +212,18 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
                 const int kind = L.ctl;
                 { LC_TIC(tq2);
                 if (VEC && kind != CTL_EVAL_COST && (a.flags & LC_FLAG_LM_MIXED)) {
-                    if (wgen) lm_eval_pass_mixed<NT, true>(a, s, l, b, n, sanitize);
-                    else lm_eval_pass_mixed<NT, false>(a, s, l, b, n, sanitize);
+                    if (wgen) lm_eval_pass_mixed<NT, true>(a, s, l, b, n, sanitize, cl);
+                    else lm_eval_pass_mixed<NT, false>(a, s, l, b, n, sanitize, cl);
                 } else if (VEC && LC_RES_PLANAR_LM) {
                     if (kind == CTL_EVAL_COST) {
-                        if (wgen) lm_eval_pass_planar<NT, false, true>(a, s, l, b, n, sanitize);
-                        else lm_eval_pass_planar<NT, false, false>(a, s, l, b, n, sanitize);
+                        if (wgen) lm_eval_pass_planar<NT, false, true>(a, s, l, b, n, sanitize, cl);
+                        else lm_eval_pass_planar<NT, false, false>(a, s, l, b, n, sanitize, cl);
                     } else {
-                        if (wgen) lm_eval_pass_planar<NT, true, true>(a, s, l, b, n, sanitize);
-                        else lm_eval_pass_planar<NT, true, false>(a, s, l, b, n, sanitize);
+                        if (wgen) lm_eval_pass_planar<NT, true, true>(a, s, l, b, n, sanitize, cl);
+                        else lm_eval_pass_planar<NT, true, false>(a, s, l, b, n, sanitize, cl);
                     }
-                } else if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(a, s, l, b, n, sanitize, xs);
-                else lm_eval_pass_res<NT, true>(a, s, l, b, n, sanitize, xs);
+                } else if (kind == CTL_EVAL_COST) lm_eval_pass_res<NT, false>(a, s, l, b, n, sanitize, xs, cl);
+                else lm_eval_pass_res<NT, true>(a, s, l, b, n, sanitize, xs, cl);
                 LC_TOC(tq2, 1); }
                 LC_TIC(tq3);
                 if (tid == 0)
@@ -197,7 +235,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             }
             solved = L.term == TERM_CONVERGENCE;
         }
-        if (tid == 0) lm_write_result<float>(a, s, b, n, solved);
+        if (tid == 0) lm_write_result<float>(a, s, b, n_total, solved, cl.leader);
         __syncthreads();
     }
 #ifdef LC_TIMING
@@ -206,20 +244,22 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
             for (int k = 0; k < 6; ++k) tr[48 + k] = (double)s.lm.tm[k]; tr[60] = live_at_start; }
         if (tid == 0) atomicAdd(&g_live_ctas[smid_], -1);
         tmem_release();
+        finish();
         return;
     }
 #else
-    if (!(MODE & MODE_LC)) { tmem_release(); return; }
+    if (!(MODE & MODE_LC)) { tmem_release(); finish(); return; }
 #endif
 
     // =========================== LC loss ===========================
-    if (VEC) lc_phase_vec<NT>(a, s, l, b, n);
+    if (VEC) lc_phase_vec<NT>(a, s, l, b, n, cl);
     else {
         const DirectWeights wsrc{static_cast<const float*>(a.weights.ptr) + b * a.weights.stride[0], a.weights.stride[1], a.weights.stride[2]};
         DirectSink sink{a, b};
         lc_phase_res<NT>(a, s, l, b, n, wsrc, sink, xs);
     }
     tmem_release();
+    finish();
 #ifdef LC_TIMING
     if (tid == 0 && a.trace) { double* tr = a.trace + (int64_t)b * (a.max_iter + 2) * 4; for (int k = 0; k < 7; ++k) tr[k] = (double)s.fin_timing[k]; tr[7] = (double)(clock64() - t_begin);
         for (int k = 0; k < 40; ++k) tr[8 + k] = (double)(s.marks[k] - s.marks[0]); tr[60] = live_at_start; }
@@ -228,27 +268,63 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2) lc_resident_kernel(cons
 }
 
 
-template <int NT, int MODE, bool TM, bool VEC>
-static int launch_res_t(const lc_args& a, cudaStream_t st, int cap, int max_smem, int tma_mask) {
-    const int n_res = cap > 0 ? cap : a.N;   // points held on chip per pose
-    const size_t smem = TM ? resident_smem_bytes_tm(n_res) : resident_smem_bytes(n_res);
+// What one launch covers: poses [pose_base, pose_base + count) of the batch, each on a cluster of `cl` CTAs (1 = one CTA per pose).
+struct ResLaunch {
+    int cap;         // > 0: ragged batch, only poses with n_points <= cap are processed here (cl == 1)
+    int max_smem, tma_mask;
+    int pose_base, count, cl;
+    int pdl;         // bit 0: trigger dependents at CTA start; bit 1: launched programmatically behind the previous kernel
+};
+
+template <int NT, int MODE, bool TM, bool VEC, int CL>
+static int launch_res_t(const lc_args& a, cudaStream_t st, const ResLaunch& r) {
+    // points held on chip per CTA
+    const int n_res = CL > 1 ? round_up4((a.N + CL - 1) / CL) : (r.cap > 0 ? r.cap : a.N);
+    const size_t smem = (TM ? resident_smem_bytes_tm(n_res) : resident_smem_bytes(n_res)) + (CL > 1 ? sizeof(ClusterShared) : 0);
     static std::atomic<bool> configured[64];   // per instantiation and per device (the opt-in smem limit is a per-device attribute)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE, TM, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        const cudaError_t e = cudaFuncSetAttribute(lc_resident_kernel<NT, MODE, TM, VEC, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, r.max_smem);
         if (e != cudaSuccess) return static_cast<int>(e);
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
-    lc_resident_kernel<NT, MODE, TM, VEC><<<a.B, NT, smem, st>>>(a, round_up4(n_res), tma_mask, cap > 0 ? cap : 0x7fffffff);
-    note_kernel("lc::lc_resident_kernel<%d,%s,%s,%s>", NT, MODE == MODE_LM ? "LM" : (MODE == MODE_LC ? "LC" : "LM|LC"), TM ? "TMEM" : "smem", VEC ? "vec4" : "scalar");
-    return static_cast<int>(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(r.count) * CL);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    unsigned na = 0;
+    if (CL > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (r.pdl & 2) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = na;
+    if (getenv("LC_B200_DEBUG_OCC")) {   // diagnostic: resident CTAs per SM / clusters per device for this launch
+        int ncl = -1, nb = -1;
+        if (CL > 1) cudaOccupancyMaxActiveClusters(&ncl, lc_resident_kernel<NT, MODE, TM, VEC, CL>, &cfg);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lc_resident_kernel<NT, MODE, TM, VEC, CL>, NT, smem);
+        fprintf(stderr, "[lc_b200] NT=%d MODE=%d CL=%d smem=%zu grid=%u: max active clusters %d, CTAs/SM %d\n", NT, MODE, CL, smem, cfg.gridDim.x, ncl, nb);
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, lc_resident_kernel<NT, MODE, TM, VEC, CL>, a, round_up4(n_res), r.tma_mask,
+                                             r.cap > 0 ? r.cap : 0x7fffffff, r.pose_base, r.pdl);
+    if (CL > 1) note_kernel("lc::lc_resident_kernel<%d,%s,smem,vec4,cluster%d>", NT, MODE == MODE_LM ? "LM" : (MODE == MODE_LC ? "LC" : "LM|LC"), CL);
+    else note_kernel("lc::lc_resident_kernel<%d,%s,%s,%s>", NT, MODE == MODE_LM ? "LM" : (MODE == MODE_LC ? "LC" : "LM|LC"), TM ? "TMEM" : "smem", VEC ? "vec4" : "scalar");
+    return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 // one (threads, mode, storage) dispatcher per translation unit
-template <bool VEC>
-static int launch_res_any(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, int cap, int max_smem, int tma_mask) {
-#define LC_RES_CASE(NT_, MODE_, TM_) return launch_res_t<NT_, MODE_, TM_, VEC>(a, st, cap, max_smem, tma_mask)
+template <bool VEC, int CL>
+static int launch_res_any(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, const ResLaunch& r) {
+#define LC_RES_CASE(NT_, MODE_, TM_) return launch_res_t<NT_, MODE_, TM_, VEC, CL>(a, st, r)
     if (mode == MODE_LM) {
         if (nt == 128) LC_RES_CASE(128, MODE_LM, false);
         if (nt == 192) LC_RES_CASE(192, MODE_LM, false);
@@ -264,7 +340,8 @@ static int launch_res_any(const lc_args& a, int mode, int nt, bool tm, cudaStrea
 #undef LC_RES_CASE
 }
 
-int launch_res_scalar(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, int cap, int max_smem, int tma_mask);
-int launch_res_vec(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, int cap, int max_smem, int tma_mask);
+int launch_res_scalar(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, const ResLaunch& r);
+int launch_res_vec(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, const ResLaunch& r);
+int launch_res_cluster2(const lc_args& a, int mode, int nt, cudaStream_t st, const ResLaunch& r);   // lc_resident_cluster.cu
 
 }  // namespace lc

@@ -4,8 +4,8 @@
 
 namespace lc {
 
-int launch_res_vec(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, int cap, int max_smem, int tma_mask) {
-    return launch_res_any<true>(a, mode, nt, tm, st, cap, max_smem, tma_mask);
+int launch_res_vec(const lc_args& a, int mode, int nt, bool tm, cudaStream_t st, const ResLaunch& r) {
+    return launch_res_any<true, 1>(a, mode, nt, tm, st, r);
 }
 
 }  // namespace lc

@@ -24,6 +24,7 @@
 
 #include "lc_resident.cuh"
 
+
 namespace lc {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -340,8 +341,8 @@ __device__ __forceinline__ void lc_thresholds2(const lc_args& a, const double* f
 
 // LC phase on the staged arrays (A = X -> q -> d/d pts3d, B = x -> ec -> d/d inv_std), one CTA per pose.  Same contract as
 // lc_phase_res.
-template <int NT>
-__device__ __forceinline__ void lc_phase_vec(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n) {
+template <int NT, class CLU>
+__device__ __forceinline__ void lc_phase_vec(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, CLU& cl) {
     const int tid = threadIdx.x;
     const VecIO io = make_vec_io(a, b);
     const bool want_any = a.g_pts3d.ptr || a.g_pts2d.ptr || a.g_weights.ptr;
@@ -359,13 +360,15 @@ __device__ __forceinline__ void lc_phase_vec(const lc_args& a, PoseShared& s, co
         float acc[4];
         lc_pass1_vec<NT>(a, s, l, io, n, tid, acc);
         block_reduce_f<4, NT>(acc, s.red, s.fin);
-        lc_thresholds1(a, s.fin, n, vcnt, d0, d1, any_clamped);
+        cl.template combine<4>(s.fin);
+        lc_thresholds1(a, s.fin, cl.n_total, vcnt, d0, d1, any_clamped);
         __syncthreads();
     }
     {
         float acc[2];
         lc_pass2_vec<NT>(l, io, n, tid, d0, d1, acc);
         block_reduce_f<2, NT>(acc, s.red, s.fin);
+        cl.template combine<2>(s.fin);
         lc_thresholds2(a, s.fin, vcnt, sq0, sq1);
         __syncthreads();
     }
@@ -374,10 +377,11 @@ __device__ __forceinline__ void lc_phase_vec(const lc_args& a, PoseShared& s, co
         float accd[48];
         lc_pass3_vec<NT>(l, io, n, tid, pc, accd);
         block_reduce_f<48, NT>(accd, s.red, s.fin);
+        cl.template combine<48>(s.fin);
     }
     LC_TOC(tq2, 4);
     { LC_TIC(tq3);
-    if (tid < 32) lc_six_fast<float>(a, s, b, want_any);
+    if (tid < 32) lc_six_fast<float>(a, s, b, want_any, cl.leader);
     __syncthreads();
     if (!want_any) return;
     LC_TOC(tq3, 5); }
@@ -535,18 +539,20 @@ __device__ __forceinline__ void lm_eval_accum_mixed(const lc_args& a, const Pose
     acc[27] = 0.5 * cost;
 }
 
-template <int NT, bool WGEN>
-__device__ __forceinline__ void lm_eval_pass_mixed(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
+template <int NT, bool WGEN, class CLU>
+__device__ __forceinline__ void lm_eval_pass_mixed(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize, CLU& cl) {
     double acc[28];
     lm_eval_accum_mixed<NT, WGEN>(a, s, l, b, n, sanitize, threadIdx.x, acc);
     block_reduce<28, NT>(acc, s.red, s.fin);
+    cl.template combine<28>(s.fin);
 }
 
-template <int NT, bool JAC, bool WGEN>
-__device__ __forceinline__ void lm_eval_pass_planar(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize) {
+template <int NT, bool JAC, bool WGEN, class CLU>
+__device__ __forceinline__ void lm_eval_pass_planar(const lc_args& a, PoseShared& s, const ResLayout& l, int b, int n, bool sanitize, CLU& cl) {
     double acc[28];
     lm_eval_accum_planar<NT, JAC, WGEN>(a, s, l, b, n, sanitize, threadIdx.x, acc);
     block_reduce<28, NT>(acc, s.red, s.fin);
+    cl.template combine<28>(s.fin);
 }
 
 }  // namespace lc

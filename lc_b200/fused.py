@@ -18,9 +18,10 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
                    bbox_3d: Tensor, *, max_iter_count=50, function_tolerance=1e-6, max_err_len=32.0, rel_thresh=3.0,
                    w_e_thresh=4.0, need=(True, False, True), grad_out: Optional[Tensor] = None, grad_scale=1.0,
                    tol_needs_success=True, out: Optional[dict] = None, force_streaming=False,
-                   loss_sum: Optional[Tensor] = None, mixed: bool = False):
+                   loss_sum: Optional[Tensor] = None, mixed: bool = False, n_points: Optional[Tensor] = None):
     """Returns dict(states, radius, invalid, iters, loss, g_pts3d, g_pts2d, g_inv_std, flags).
 
+    ``n_points`` (B,) int32: ragged batch padded to N (only the first n_points[b] correspondences of pose b count).
     ``out`` may carry preallocated output tensors from a previous call (same shapes) to avoid allocation.
     ``mixed`` (opt-in) lets the resident kernels form the Jacobian sums of the solve in packed fp32 (``LC_FLAG_LM_MIXED``):
     residuals, cost and every trust-region decision stay fp64; over 10 240 poses the iteration counts, accept / reject sequences
@@ -29,7 +30,7 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
     (the linear term vanishes at the optimum, so the loss is that sensitive there), which is outside this repo's own 1e-5 bar for
     the fused operator although inside every north-star tolerance.
     """
-    dev = nat.check_cuda(K, start, pts3d, pts2d, inv_std, valid, bbox_3d, grad_out)
+    dev = nat.check_cuda(K, start, pts3d, pts2d, inv_std, valid, bbox_3d, grad_out, n_points)
     dt = pts3d.dtype
     B, N = pts3d.shape[:2]
     o = out or {}
@@ -55,6 +56,6 @@ def solve_and_loss(K: Tensor, start: Tensor, pts3d: Tensor, pts2d: Tensor, inv_s
                          state=res["states"], radius=res["radius"], invalid=res["invalid"], iters=res["iters"],
                          lc_flags=res["flags"], flags=flags, weight_mode=nat.W_INV_STD, max_iter=int(max_iter_count),
                          function_tolerance=ftol, max_err_len=float(max_err_len), rel_thresh=float(rel_thresh),
-                         w_e_thresh=float(w_e_thresh), grad_scale=float(grad_scale), loss_sum=loss_sum)
+                         w_e_thresh=float(w_e_thresh), grad_scale=float(grad_scale), loss_sum=loss_sum, n_points=n_points)
     res["launches"] = nat.call("lc_b200_solve_loss", args, dev)
     return res

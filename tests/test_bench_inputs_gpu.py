@@ -44,7 +44,7 @@ def test_p3_bench_inputs_match_the_oracle(oracle, bench_inputs):
     go = torch.full((B,), 1.0 / B, dtype=torch.float32, device="cuda")
     o = solve_and_loss(d["K"], d["start"], p3, p2, s, None, d["bbox"], need=(True, False, True), grad_out=go)
     torch.cuda.synchronize()
-    assert o["launches"] == 1 and b"LM|LC" in nat.lib().lc_b200_last_kernels()
+    assert o["launches"] in (1, 2) and b"LM|LC" in nat.lib().lc_b200_last_kernels()   # 2: the last wave runs as two-CTA clusters
     ref = oracle.p3(c.K[idx], c.pts3d[idx], c.pts2d[idx], c.inv_std[idx], c.bbox_3d[idx], c.start[idx])
     assert np.array_equal(o["invalid"].cpu().numpy()[idx], ref["invalid"]) and not ref["invalid"].any()
     assert np.array_equal(o["iters"].cpu().numpy()[idx], ref["iters"])

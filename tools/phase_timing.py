@@ -41,7 +41,7 @@ def run(pipeline):
     g3, gs = nat.empty_like_dense(X), nat.empty_like_dense(s)
     mode = dict(p1="lc_b200_loss_fwd_bwd", p2="lc_b200_lm_solve", p3="lc_b200_solve_loss")[pipeline]
     kw = dict(K=c.K, pose=c.pose if pipeline == "p1" else c.start, pts3d=X, pts2d=x, weights=s, bbox=c.bbox_3d, trace=trace,
-              weight_mode=nat.W_INV_STD, flags=nat.FLAG_TOL_NEEDS_SUCCESS)
+              weight_mode=nat.W_INV_STD, flags=nat.FLAG_TOL_NEEDS_SUCCESS | (nat.FLAG_LM_MIXED if os.environ.get("LC_TIMING_MIXED") else 0))
     if pipeline != "p1":
         kw.update(state=st, radius=rad, invalid=inv, iters=it)
     if pipeline != "p2":

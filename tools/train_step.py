@@ -7,6 +7,8 @@ the reference files staged under baseline/_ref (tools/stage_reference.py; they a
   arm "ours"       lc_b200.cov_mixed.Loss_cov_mixed swapped in for that one name (the import-line swap of INTEGRATION.md §1),
   arm "fused"      additionally lc_b200.dense.dense_pose_loss* in place of the producer glue of Loss_fn.dense_pose_loss (row f1/f3),
   arm "nopose"     w_loss_pose = 0 (the step without the LC loss: the LC op's share = 1 - t_nopose / t_arm).
+  arm "nolc"       the LC op replaced by a zero-valued differentiable stand-in, glue and hooks alive (what DDP runs use: with
+                   w_loss_pose = 0 DDP hands None to the reference's tensor hooks).
 Random-init networks (the pretrained resnet34 file is replaced by a random state dict in memory), synthetic blobs with the keys
 of dataset.py:451-473 built from a consistent pose / camera / surface so that every loss term is finite and active.
 
@@ -160,8 +162,13 @@ def main():
         opt.step()
         return loss
 
+    def nolc(K, pose, pts3d, pts2d, inv_std, valid=None, **kw):
+        # arm "nolc": the step with the LC op itself removed but its glue and hooks alive (zero loss, zero gradients).  Under DDP the
+        # "nopose" arm (w_loss_pose = 0) leaves head outputs unused and the reference's tensor hooks then receive None.
+        return (pts3d.sum((1, 2)) + inv_std.sum((1, 2))) * 0
+
     def set_arm(arm):
-        losses.Loss_cov_mixed = ref_lc if arm == "reference" else ours_lc      # the one-name swap
+        losses.Loss_cov_mixed = ref_lc if arm == "reference" else (nolc if arm == "nolc" else ours_lc)      # the one-name swap
         losses.Loss_fn.dense_pose_loss = fused_dense_pose_loss if arm == "fused" else ref_dense
         cfg.loss.w_loss_pose = 0 if arm == "nopose" else w_pose
 
@@ -212,7 +219,7 @@ def main():
         res["vs_float64_reference"] = {arm: dict(loss_pose_rel=abs(pr["loss_pose"] - p64["loss_pose"]) / abs(p64["loss_pose"]),
                                                  grad_rel_l2_all_parameters=math.sqrt(sum(float((pr["grads"][k].double() - p64["grads"][k]).pow(2).sum())
                                                                                        for k in p64["grads"])) / den)
-                                       for arm, pr in probes.items() if arm != "nopose" and "grads" in pr}
+                                       for arm, pr in probes.items() if arm not in ("nopose", "nolc") and "grads" in pr}
         del model, net, opt
         torch.cuda.empty_cache()
     restore()
@@ -226,10 +233,11 @@ def main():
                                                   grad_rel_l2_at_network_outputs=og, grad_rel_l2_all_parameters=num / den,
                                                   note="same weights, inputs and sub-sampling offsets; the parameter gradients pass through the same "
                                                        "cuDNN backward in both arms, which amplifies the 1e-6-level differences of the op's input gradients")
-    if "nopose" in res:
-        for arm in ("reference", "ours", "fused"):
-            if arm in res:
-                res[arm]["lc_share_of_step"] = 1 - res["nopose"]["ms_per_step"] / res[arm]["ms_per_step"]
+    for base, key in (("nopose", "lc_share_of_step"), ("nolc", "lc_op_share_of_step")):
+        if base in res:
+            for arm in ("reference", "ours", "fused"):
+                if arm in res:
+                    res[arm][key] = 1 - res[base]["ms_per_step"] / res[arm]["ms_per_step"]
     H, W = blob["msk_vis"].shape[-2:]
     sample = cfg.loss.pose_loss_cfg.get("dense_sample", 2)
     line = dict(config=a.config, batch_per_gpu=a.batch, n_gpus=world, ddp=bool(a.ddp and world > 1), steps=a.steps, out_hw=[H, W], dense_sample=sample,
