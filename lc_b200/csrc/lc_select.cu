@@ -9,37 +9,64 @@
 //
 // The per-sample quantile is an exact order statistic: 4-pass 8-bit radix select over the fp32 bit patterns held in
 // shared memory (values are >= 0, so the bit patterns are ordered), followed by torch's fp32 lerp.
+//
+// Round 2: the same one-CTA-per-sample structure with its serial pieces removed — warp-aggregated histogram atomics (the keys of a
+// sample share their leading byte, plain atomics serialised 32-way), warp-scan bin search, one scan over all (round, warp) cells
+// for the compaction instead of three barriers per 1024 pixels, 16-byte loads for the softmax statistics and 16-byte stores for
+// the zero padding (the padding is most of the written bytes).  profiles/README.md has the before / after.
 #include <atomic>
 
 #include "lc_resident.cuh"
 
 namespace lc {
 
-constexpr int kSelNT = 1024;
+// 512 threads x 46 registers: two CTAs per SM (1024 threads allowed one, and B = 256 samples then ran as two waves on 148 SMs)
+constexpr int kSelNT = 512;
 
 __device__ __forceinline__ float sel_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
-// value of the rank-k (0-based) smallest key among u[0..n) and of its successor in sorted order; all threads call
+// value of the rank-k (0-based) smallest key among u[0..n) and of its successor in sorted order; all threads call.
+// Four 8-bit passes.  The keys of one sample share their leading bits (similar magnitudes), so a plain shared-memory atomicAdd
+// per key serialises on a handful of bins: the lanes of a warp that hit the same bin are aggregated with match.any first (one
+// atomic per distinct bin and warp).  The bin scan is a warp scan over 32 x 8 bins instead of one thread walking 256 counters.
 __device__ void radix_select_pair(const unsigned* u, int n, int k, unsigned* hist, unsigned* bc, unsigned& kth, unsigned& next) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned prefix = 0, mask = 0;
     int kk = k;
+    for (int j = tid; j < 256; j += kSelNT) hist[j] = 0;
+    __syncthreads();
+    const int n_up = (n + 31) & ~31;   // warp-uniform trip count (match.any is warp-collective)
     for (int pass = 3; pass >= 0; --pass) {
-        for (int j = tid; j < 256; j += kSelNT) hist[j] = 0;
-        __syncthreads();
         const int sh = 8 * pass;
-        for (int i = tid; i < n; i += kSelNT)
-            if ((u[i] & mask) == prefix) atomicAdd(&hist[(u[i] >> sh) & 255u], 1u);
+        for (int i = tid; i < n_up; i += kSelNT) {
+            const unsigned v = i < n ? u[i] : 0u;
+            const bool act = i < n && (v & mask) == prefix;
+            const unsigned key = act ? ((v >> sh) & 255u) : 0xFFFFu;
+            const unsigned peers = __match_any_sync(kFull, key);
+            if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[key], static_cast<unsigned>(__popc(peers)));
+        }
         __syncthreads();
-        if (tid == 0) {
-            unsigned cum = 0;
-            int bin = 0;
-            for (; bin < 256; ++bin) {
-                if (cum + hist[bin] > static_cast<unsigned>(kk)) break;
-                cum += hist[bin];
+        if (tid < 32) {
+            unsigned c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; sum += c[j]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+            const unsigned excl = incl - sum, want = static_cast<unsigned>(kk);
+            if (excl <= want && want < incl) {   // exactly one lane: the one whose eight bins contain rank kk
+                unsigned cum = excl;
+                int bin = 8 * lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + c[j] > want) break;
+                    cum += c[j]; ++bin;
+                }
+                bc[0] = static_cast<unsigned>(bin);
+                bc[1] = cum;
             }
-            bc[0] = static_cast<unsigned>(bin);
-            bc[1] = cum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hist[8 * lane + j] = 0;   // ready for the next pass
         }
         __syncthreads();
         prefix |= bc[0] << sh;
@@ -56,14 +83,31 @@ __device__ void radix_select_pair(const unsigned* u, int n, int k, unsigned* his
         const unsigned v = u[i];
         if (v <= kth) ++cle; else mn = min(mn, v);
     }
-    atomicAdd(&bc[0], cle);
-    atomicMin(&bc[1], mn);
+    cle = __reduce_add_sync(kFull, cle);
+    mn = __reduce_min_sync(kFull, mn);
+    if (lane == 0) { atomicAdd(&bc[0], cle); atomicMin(&bc[1], mn); }
     __syncthreads();
     next = (bc[0] >= static_cast<unsigned>(k) + 2u || bc[1] == 0xFFFFFFFFu) ? kth : bc[1];
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args d) {
+// zero the floats [beg, end) of a contiguous array: 16-byte stores in the aligned middle
+__device__ __forceinline__ void zero_flat(float* p, int64_t beg, int64_t end, int tid) {
+    if (beg >= end) return;
+    const int64_t mis = (reinterpret_cast<uintptr_t>(p + beg) >> 2) & 3;
+    int64_t a0 = beg + ((4 - mis) & 3);
+    if (a0 > end) a0 = end;
+    const int64_t a1 = a0 + ((end - a0) & ~int64_t(3));
+    if (tid < a0 - beg) p[beg + tid] = 0.f;
+    if (tid < end - a1) p[a1 + tid] = 0.f;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* q = reinterpret_cast<float4*>(p + a0);
+    for (int64_t j = tid; j < ((a1 - a0) >> 2); j += kSelNT) q[j] = z;
+}
+
+constexpr int kSelMaxRounds = 96;   // N <= 96 * 512 sampled pixels per sample (shared memory holds 5 B each: <= ~45 k anyway)
+
+__global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_args d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Hn = (d.H + d.sample - 1) / d.sample, Wn = (d.W + d.sample - 1) / d.sample, N = Hn * Wn, HW = d.H * d.W;
     float* vals = reinterpret_cast<float*>(smem_raw);                    // [N] quantile operand
@@ -73,7 +117,8 @@ __global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args 
     __shared__ float redf[kSelNT / 32 * 2];
     __shared__ int wsum[kSelNT / 32];
     __shared__ float sm_stat[4];
-    __shared__ int s_base;
+    constexpr int NW = kSelNT / 32;
+    __shared__ int cnts[kSelMaxRounds * NW + 32];   // per (round, warp) selected counts -> exclusive offsets; [R * NW] = total
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- softmax statistics (test.py:84-88): joint over 2*H*W for a (B,1,1,1) scale, per channel for (B,2,1,1) ----
@@ -82,21 +127,43 @@ __global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args 
     const int64_t lgc = fused ? d.logits.stride[1] : 0;
     float m0 = 0.f, m1 = 0.f, k0 = 1.f, k1 = 1.f;
     if (fused) {
+        // both planes are contiguous (lc_abi.cu checks): 16-byte loads when the planes are 16-byte aligned
+        const bool v4 = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0 && (lgc & 3) == 0;
         float mx0 = -INFINITY, mx1 = -INFINITY;
-        for (int j = tid; j < HW; j += kSelNT) { mx0 = fmaxf(mx0, lg[j]); mx1 = fmaxf(mx1, lg[lgc + j]); }
+        if (v4) {
+            const float4* p0 = reinterpret_cast<const float4*>(lg);
+            const float4* p1 = reinterpret_cast<const float4*>(lg + lgc);
+            for (int j = tid; j < (HW >> 2); j += kSelNT) {
+                const float4 a = __ldg(p0 + j), c = __ldg(p1 + j);
+                mx0 = fmaxf(mx0, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+                mx1 = fmaxf(mx1, fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)));
+            }
+        } else {
+            for (int j = tid; j < HW; j += kSelNT) { mx0 = fmaxf(mx0, lg[j]); mx1 = fmaxf(mx1, lg[lgc + j]); }
+        }
         for (int o = 16; o > 0; o >>= 1) { mx0 = fmaxf(mx0, __shfl_xor_sync(kFull, mx0, o)); mx1 = fmaxf(mx1, __shfl_xor_sync(kFull, mx1, o)); }
         if (lane == 0) { redf[warp * 2] = mx0; redf[warp * 2 + 1] = mx1; }
         __syncthreads();
-        if (tid == 0) {
-            float a0 = redf[0], a1 = redf[1];
-            for (int w = 1; w < kSelNT / 32; ++w) { a0 = fmaxf(a0, redf[w * 2]); a1 = fmaxf(a1, redf[w * 2 + 1]); }
+        if (tid < 32) {
+            float a0 = lane < kSelNT / 32 ? redf[lane * 2] : -INFINITY, a1 = lane < kSelNT / 32 ? redf[lane * 2 + 1] : -INFINITY;
+            for (int o = 16; o > 0; o >>= 1) { a0 = fmaxf(a0, __shfl_xor_sync(kFull, a0, o)); a1 = fmaxf(a1, __shfl_xor_sync(kFull, a1, o)); }
             if (d.scale_dim == 1) a0 = a1 = fmaxf(a0, a1);
-            sm_stat[0] = a0; sm_stat[1] = a1;
+            if (lane == 0) { sm_stat[0] = a0; sm_stat[1] = a1; }
         }
         __syncthreads();
         m0 = sm_stat[0]; m1 = sm_stat[1];
         float s0 = 0.f, s1 = 0.f;
-        for (int j = tid; j < HW; j += kSelNT) { s0 += expf(lg[j] - m0); s1 += expf(lg[lgc + j] - m1); }
+        if (v4) {
+            const float4* p0 = reinterpret_cast<const float4*>(lg);
+            const float4* p1 = reinterpret_cast<const float4*>(lg + lgc);
+            for (int j = tid; j < (HW >> 2); j += kSelNT) {
+                const float4 a = __ldg(p0 + j), c = __ldg(p1 + j);
+                s0 += (expf(a.x - m0) + expf(a.y - m0)) + (expf(a.z - m0) + expf(a.w - m0));
+                s1 += (expf(c.x - m1) + expf(c.y - m1)) + (expf(c.z - m1) + expf(c.w - m1));
+            }
+        } else {
+            for (int j = tid; j < HW; j += kSelNT) { s0 += expf(lg[j] - m0); s1 += expf(lg[lgc + j] - m1); }
+        }
         for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(kFull, s0, o); s1 += __shfl_xor_sync(kFull, s1, o); }
         __syncthreads();
         if (lane == 0) { redf[warp * 2] = s0; redf[warp * 2 + 1] = s1; }
@@ -122,6 +189,7 @@ __global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args 
 
     // ---- per sampled pixel: segmentation flag and the quantile operand ----
     int cnt = 0;
+#pragma unroll 4
     for (int i = tid; i < N; i += kSelNT) {
         const int yq = i / Wn, xq = i - yq * Wn, y = yq * d.sample, x = xq * d.sample;
         const bool m = sel_sigmoid(ml[y * d.msk_logits.stride[1] + x * d.msk_logits.stride[2]]) > d.seg_thresh;   // test.py:70
@@ -164,9 +232,14 @@ __global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args 
     float n3[3] = {1.f, 1.f, 1.f};
     if (d.noc_scale.ptr)
         for (int k = 0; k < 3; ++k) n3[k] = ldf(d.noc_scale, b * d.noc_scale.stride[0] + k * d.noc_scale.stride[1]);
-    if (tid == 0) s_base = 0;
-    __syncthreads();
     const bool take_all = N <= d.min_points;   // select_valid: `t[...] if len(t) > min_cnt else t`
+    auto keep = [&](int i) {
+        if (i >= N) return false;
+        if (take_all) return true;
+        if (d.mode == LC_SEL_MASK) return mflag[i] != 0;
+        if (d.mode == LC_SEL_QUANTILE) return vals[i] >= thr;
+        return (vals[i] >= thr) && mflag[i] != 0;
+    };
     auto emit = [&](int slot, int i) {
         const int yq = i / Wn, xq = i - yq * Wn, y = yq * d.sample, x = xq * d.sample;
         float w0, w1;
@@ -179,26 +252,36 @@ __global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args 
         stf(d.inv_cov, oc, w0 * w0); stf(d.inv_cov, oc + d.inv_cov.stride[2], w1 * w1);
         if (d.index) d.index[static_cast<int64_t>(b) * d.Nmax + slot] = i;
     };
-    for (int i0 = 0; i0 < N; i0 += kSelNT) {
-        const int i = i0 + tid;
-        bool v = false;
-        if (i < N) {
-            if (take_all) v = true;
-            else if (d.mode == LC_SEL_MASK) v = mflag[i] != 0;
-            else if (d.mode == LC_SEL_QUANTILE) v = vals[i] >= thr;
-            else v = (vals[i] >= thr) && mflag[i] != 0;
-        }
-        const unsigned bal = __ballot_sync(kFull, v);
-        if (lane == 0) wsum[warp] = __popc(bal);
-        __syncthreads();
-        int off = s_base;
-        for (int w = 0; w < warp; ++w) off += wsum[w];
-        if (v) emit(off + __popc(bal & ((1u << lane) - 1u)), i);
-        __syncthreads();
-        if (tid == 0) { int t = 0; for (int w = 0; w < kSelNT / 32; ++w) t += wsum[w]; s_base += t; }
-        __syncthreads();
+    // counts of every (round, warp) cell first, one scan over them, then every thread knows its output slot: three barriers in
+    // total instead of three per round of 1024 pixels
+    const int R = (N + kSelNT - 1) / kSelNT;
+    for (int r = 0; r < R; ++r) {
+        const unsigned bal = __ballot_sync(kFull, keep(r * kSelNT + tid));
+        if (lane == 0) cnts[r * NW + warp] = __popc(bal);
     }
-    int total = s_base;
+    __syncthreads();
+    if (tid < 32) {
+        int carry = 0;
+        const int cells = R * NW;
+        for (int c0 = 0; c0 < cells; c0 += 32) {
+            const int v = c0 + lane < cells ? cnts[c0 + lane] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+            if (c0 + lane < cells) cnts[c0 + lane] = carry + incl - v;
+            carry += __shfl_sync(kFull, incl, 31);
+        }
+        if (lane == 0) cnts[cells] = carry;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < R; ++r) {
+        const int i = r * kSelNT + tid;
+        const bool v = keep(i);
+        const unsigned bal = __ballot_sync(kFull, v);
+        if (v) emit(cnts[r * NW + warp] + __popc(bal & ((1u << lane) - 1u)), i);
+    }
+    int total = cnts[R * NW];
     // fewer than min_points selected: pad with indices drawn from all N points (test.py:108-113 uses np.random.choice; here a
     // per-sample LCG — same distribution, different stream)
     if (!take_all && total < d.min_points) {
@@ -210,14 +293,17 @@ __global__ void __launch_bounds__(kSelNT) lc_select_kernel(const lc_select_args 
         total = d.min_points;
     }
     if (tid == 0) d.n_points[b] = total;
-    // zero padding up to Nmax
-    for (int slot = total + tid; slot < d.Nmax; slot += kSelNT) {
-        const int64_t o3 = b * d.pts3d.stride[0] + slot * d.pts3d.stride[1], o2 = b * d.pts2d.stride[0] + slot * d.pts2d.stride[1],
-                      oc = b * d.inv_cov.stride[0] + slot * d.inv_cov.stride[1];
-        for (int k = 0; k < 3; ++k) stf(d.pts3d, o3 + k * d.pts3d.stride[2], 0.f);
-        for (int k = 0; k < 2; ++k) { stf(d.pts2d, o2 + k * d.pts2d.stride[2], 0.f); stf(d.inv_cov, oc + k * d.inv_cov.stride[2], 0.f); }
-        if (d.index) d.index[static_cast<int64_t>(b) * d.Nmax + slot] = -1;
-    }
+    // zero padding up to Nmax: 16-byte stores when an output is contiguous in (slot, component) — the usual (B,Nmax,C) tensors —
+    // else element by element through the strides
+    auto zero_out = [&](const lc_view& v, int C) {
+        float* base = static_cast<float*>(v.ptr) + b * v.stride[0];
+        if (v.stride[2] == 1 && v.stride[1] == C) { zero_flat(base, static_cast<int64_t>(total) * C, static_cast<int64_t>(d.Nmax) * C, tid); return; }
+        for (int slot = total + tid; slot < d.Nmax; slot += kSelNT)
+            for (int k = 0; k < C; ++k) base[slot * v.stride[1] + k * v.stride[2]] = 0.f;
+    };
+    zero_out(d.pts3d, 3); zero_out(d.pts2d, 2); zero_out(d.inv_cov, 2);
+    if (d.index)
+        for (int slot = total + tid; slot < d.Nmax; slot += kSelNT) d.index[static_cast<int64_t>(b) * d.Nmax + slot] = -1;
 }
 
 // cudaError_t as int, or -1 when the sampled point count does not fit in shared memory
@@ -227,10 +313,10 @@ int launch_select(const lc_select_args& d, cudaStream_t st) {
     int dev = 0, max_smem = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return static_cast<int>(cudaGetLastError());
-    if (smem + 4096 > static_cast<size_t>(max_smem)) return -1;
+    if (smem + 16384 > static_cast<size_t>(max_smem) || N > kSelMaxRounds * kSelNT) return -1;
     static std::atomic<bool> configured[64];
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        const cudaError_t e = cudaFuncSetAttribute(lc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 4096);
+        const cudaError_t e = cudaFuncSetAttribute(lc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 16384);
         if (e != cudaSuccess) return static_cast<int>(e);
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
