@@ -16,6 +16,7 @@ if [ "$1" = "ncu" ]; then
 for p in p3 p1 p2; do
 ncu --set full --clock-control none --import-source on -k regex:lc_resident -s 6 -c 1 -f -o gpurun_out/prof_${R}_final_$p python bench.py --pipeline $p --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b_ncu_$p.log 2>&1
 done
+ncu --set full --clock-control none --import-source on -k regex:lc_select -s 2 -c 1 -f -o gpurun_out/prof_${R}_select python tools/bench_producers.py --no-cpu > gpurun_out/b_ncu_select.log 2>&1
 fi
 python tools/bench_tiny.py --out gpurun_out/bench_tiny_$R.json > gpurun_out/b_tiny.log 2>&1
 python tools/bench_reference_gpu.py --out gpurun_out/reference_gpu_$R.json > gpurun_out/b_refgpu.log 2>&1
@@ -25,6 +26,9 @@ python tools/train_step.py --config zycbv --steps 20 --out gpurun_out/train_step
 python tools/sweep.py --cpu --out gpurun_out/sweep_$R.md > gpurun_out/b_sweep.log 2>&1
 python tools/bench_producers.py --out gpurun_out/bench_producers_$R.json > gpurun_out/b_prod.log 2>&1
 python tools/bench_dense.py > gpurun_out/bench_dense_$R.json 2> gpurun_out/b_dense.err
+python bench.py --pipeline p3 --lm-mixed --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/bench_${R}_p3_mixed.json 2>/dev/null
+python bench.py --pipeline p2 --lm-mixed --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/bench_${R}_p2_mixed.json 2>/dev/null
+bash tools/ab_batch.sh "p3" "cluster64:64:LC_B200_SPLIT=1 single64:64:LC_B200_SPLIT=0 cluster1024:1024:LC_B200_SPLIT=1 single1024:1024:LC_B200_SPLIT=0" > gpurun_out/cluster_split_${R}.txt 2>&1
 LC_B200_PERSIST=1 python bench.py --pipeline p3 --steps 60 --no-cpu-baseline --no-e2e > gpurun_out/bench_${R}_p3_persist.json 2>/dev/null
 LC_B200_PERSIST=1 python bench.py --pipeline p1 --steps 60 --no-cpu-baseline --no-e2e > gpurun_out/bench_${R}_p1_persist.json 2>/dev/null
 cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/sanitizer_$R.txt
