@@ -61,11 +61,15 @@ enum {
     LC_FLAG_TOL_NEEDS_SUCCESS = 2, /* solver: Ceres >= 2.1 "atleast_one_successful_step" guard (see oracle/lm_oracle.c) */
     LC_FLAG_EXACT_HESSIAN = 4,     /* pnp_jac_cov(_bwd): add the r * d2r term of hessian_6d_elem (pnp_auto.py:59-83); needs pts2d */
     LC_FLAG_FORCE_STREAMING = 8,   /* per-pose entry points: always use the streaming fp64 kernel (tests / A-B comparisons)  */
-    LC_FLAG_LM_MIXED = 16          /* solver, resident kernels with planar fp32 weights: residuals, cost and every trust-region decision
+    LC_FLAG_LM_MIXED = 16,         /* solver, resident kernels with planar fp32 weights: residuals, cost and every trust-region decision
                                       in fp64 as always, but the Jacobian rows and their sums J^T J, J^T r in packed fp32 per thread (fp64
                                       across threads).  Moves ~3/4 of the pass off the fp64 pipe.  The iterates differ from the all-fp64
                                       pass by ~1e-6 of a step (<< the 1e-6 rad tolerance); profiles/lm_mixed_check_r2.md holds the
                                       iteration-count / accept-flag comparison over 10k poses.  Opt-in; ignored by the other kernels. */
+    LC_FLAG_COV_2D = 32            /* loss: Loss_cov_mixed(..., cov_2d=True) (lib/cov_mixed.py:76-80, 91-97): the corner covariances and the
+                                      linear term are those of the PROJECTED bbox corners (8 x 2 rows through project_apply) instead of
+                                      the 3-D ones (8 x 3).  No reference config enables it; served by the streaming kernel only
+                                      (lc_b200_loss_fwd_bwd; the fused / dense entry points reject it). */
 };
 
 /* per-pose status bits written to `lc_flags` */

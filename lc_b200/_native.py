@@ -27,7 +27,7 @@ BUILD_DIR = os.path.join(_HERE, "csrc", "build")
 ABI_VERSION = 2
 LC_F32, LC_F64 = 0, 1
 W_ICOV_DIAG, W_ICOV_FULL, W_INV_STD, W_SQRT_L = 0, 1, 2, 3
-FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN, FLAG_FORCE_STREAMING, FLAG_LM_MIXED = 1, 2, 4, 8, 16
+FLAG_NAN_TO_NUM, FLAG_TOL_NEEDS_SUCCESS, FLAG_EXACT_HESSIAN, FLAG_FORCE_STREAMING, FLAG_LM_MIXED, FLAG_COV_2D = 1, 2, 4, 8, 16, 32
 ST_HESS_NOT_SPD, ST_PRIOR_NOT_GOOD, ST_COV_NOT_GOOD = 1, 2, 4
 
 EXPORTS = ("lc_b200_abi_version", "lc_b200_last_error", "lc_b200_last_launch_count", "lc_b200_lm_solve",

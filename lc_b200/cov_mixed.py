@@ -26,9 +26,10 @@ def _as_batched(t: Tensor, tail: int):
 def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std: Tensor, valid: Optional[Tensor],
                  bbox_3d: Tensor, *, max_err_len=32.0, rel_thresh=3.0, w_e_thresh=4.0, need=(True, True, True),
                  grad_out: Optional[Tensor] = None, grad_scale: float = 1.0, want_cov=False,
-                 force_streaming=False, loss_sum: Optional[Tensor] = None, n_points: Optional[Tensor] = None):
+                 force_streaming=False, loss_sum: Optional[Tensor] = None, n_points: Optional[Tensor] = None, cov_2d: bool = False):
     """One launch: per-pose loss and d loss/d (pts3d, pts2d, inv_std) scaled by grad_scale*grad_out[b].
 
+    ``cov_2d``: the projected-bbox variant of the reference (``lib/cov_mixed.py:76-80, 91-97``; streaming kernel).
     ``n_points`` (B,) int32: ragged batch padded to N, only the first n_points[b] correspondences of pose b count (the padding
     gets zero gradients), like ``lm_solve``.
 
@@ -55,7 +56,8 @@ def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std:
                          bbox=bbox_3d, grad_out=grad_out, loss=loss, g_pts3d=g3, g_pts2d=g2, g_weights=gs,
                          cov=cov, update_cov=ucov, lc_flags=flags, max_err_len=float(max_err_len),
                          rel_thresh=float(rel_thresh), w_e_thresh=float(w_e_thresh), grad_scale=float(grad_scale),
-                         flags=nat.FLAG_FORCE_STREAMING if force_streaming else 0, loss_sum=loss_sum, n_points=n_points)
+                         flags=(nat.FLAG_FORCE_STREAMING if force_streaming else 0) | (nat.FLAG_COV_2D if cov_2d else 0),
+                         loss_sum=loss_sum, n_points=n_points)
     nat.call("lc_b200_loss_fwd_bwd", args, dev)
     out = dict(loss=loss, g_pts3d=g3, g_pts2d=g2, g_inv_std=gs, flags=flags)
     if want_cov:
@@ -65,10 +67,10 @@ def loss_fwd_bwd(K: Tensor, pose: Tensor, pts3d: Tensor, pts2d: Tensor, inv_std:
 
 class _LossCovMixed(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pts3d, pts2d, inv_std, K, pose, valid, bbox_3d, max_err_len, rel_thresh, w_e_thresh):
+    def forward(ctx, pts3d, pts2d, inv_std, K, pose, valid, bbox_3d, max_err_len, rel_thresh, w_e_thresh, cov_2d=False):
         need = tuple(ctx.needs_input_grad[:3])
         out = loss_fwd_bwd(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, max_err_len=max_err_len,
-                           rel_thresh=rel_thresh, w_e_thresh=w_e_thresh, need=need)
+                           rel_thresh=rel_thresh, w_e_thresh=w_e_thresh, need=need, cov_2d=cov_2d)
         # the fused launch already produced d loss_b / d input; they live as long as the graph does (backward may run more
         # than once under retain_graph=True, like the reference's autograd graph)
         ctx.grads = (out["g_pts3d"], out["g_pts2d"], out["g_inv_std"])
@@ -87,7 +89,7 @@ class _LossCovMixed(torch.autograd.Function):
             g = g * go
             # inputs that were broadcast over the batch (e.g. the shared pixel grid) get the summed gradient
             res.append(g if g.shape == shp else g.sum_to_size(shp))
-        return (*res, None, None, None, None, None, None, None)
+        return (*res, None, None, None, None, None, None, None, None)
 
 
 def Loss_cov_mixed(K_out: Tensor, pose_gt: Tensor, pts3d: Tensor, pts2d_out: Tensor, inv_std2d: Tensor,
@@ -95,12 +97,12 @@ def Loss_cov_mixed(K_out: Tensor, pose_gt: Tensor, pts3d: Tensor, pts2d_out: Ten
     """Same contract as the reference ``Loss_cov_mixed`` (``lib/cov_mixed.py:100-150``).
 
     kwargs: ``bbox_3d`` (required), ``max_err_len=32``, ``rel_thresh=3``, ``w_e_thresh=4``,
-    ``cov_2d=False`` (the projected-corner variant no reference config enables; not implemented).
+    ``cov_2d=False`` (``True``: the projected-corner variant, ``lib/cov_mixed.py:76-80, 91-97``; no reference config enables it,
+    it runs on the generic streaming kernel).
     Returns the per-sample loss with the leading shape of the inputs.
     """
     bbox_3d = kwargs["bbox_3d"]
-    if kwargs.get("cov_2d", False):
-        raise NotImplementedError("cov_2d=True is not enabled by any reference config and is not implemented")
+    cov_2d = bool(kwargs.get("cov_2d", False))
     max_err_len = kwargs.get("max_err_len", 32)
     if isinstance(max_err_len, Tensor):
         raise NotImplementedError("tensor-valued max_err_len is not supported")
@@ -113,5 +115,5 @@ def Loss_cov_mixed(K_out: Tensor, pose_gt: Tensor, pts3d: Tensor, pts2d_out: Ten
     bb = bbox_3d.expand(lead + (8, 3)).reshape(B, 8, 3)
     v = None if valid_factor is None else valid_factor.detach().expand(pts3d.shape[:-1]).reshape(B, -1)
     loss = _LossCovMixed.apply(p3, p2, s, K.detach(), pose, v, bb.detach(), float(max_err_len),
-                               float(kwargs.get("rel_thresh", 3)), float(kwargs.get("w_e_thresh", 4)))
+                               float(kwargs.get("rel_thresh", 3)), float(kwargs.get("w_e_thresh", 4)), cov_2d)
     return loss.reshape(lead)

@@ -53,6 +53,10 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
     if (mode == (MODE_LM | MODE_LC) && a->weight_mode != LC_W_INV_STD)
         return fail(LC_E_BADARG, "solve_loss takes inverse std weights (weight_mode = LC_W_INV_STD)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (a->flags & LC_FLAG_COV_2D) {   // the projected-corner variant lives in the streaming kernel's 6x6 sections only
+        if (mode != MODE_LC) return fail(LC_E_BADARG, "LC_FLAG_COV_2D is a flag of lc_b200_loss_fwd_bwd");
+        return check_launch(launch_stream_pose(*a, mode, st));
+    }
     // sparse keypoints (N <= 32): one thread per pose, the serial 6x6 / trust-region sections of 32 poses run in parallel (lc_tiny.cu)
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && a->N <= kTinyMaxN) return check_launch(launch_tiny_pose(*a, mode, st));
     // large N, many poses, planar slabs: the persistent pipelined kernel (one CTA per SM, two poses in flight, lc_persist.cu)

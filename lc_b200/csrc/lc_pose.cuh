@@ -408,6 +408,29 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
             s.rows[tid * 6 + 3 + cc] = (r == cc) ? 1.0 : 0.0;
         }
     }
+    const int nd = (a.flags & LC_FLAG_COV_2D) ? 2 : 3;   // coordinates per bbox corner
+    if (nd == 2) {
+        // cov_2d (cov_mixed.py:76-80, 91-97): rows of the PROJECTED corners, xform_2d = project_apply(K, R c + t) (transforms.py:47-63):
+        // row2d[j][a] = sum_k dproj_a/dP_k row3d[j][k],  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z > 0.1]) / max(z, 0.1)
+        __syncthreads();
+        double r2[6] = {0, 0, 0, 0, 0, 0};
+        if (tid < 16) {
+            const int j = tid >> 1, a2 = tid & 1;
+            const double* c = s.bbox + 3 * j;
+            double P[3], KP[3];
+            for (int r = 0; r < 3; ++r) P[r] = s.R[r * 3] * c[0] + s.R[r * 3 + 1] * c[1] + s.R[r * 3 + 2] * c[2] + s.t[r];
+            for (int r = 0; r < 3; ++r) KP[r] = s.K[r * 3] * P[0] + s.K[r * 3 + 1] * P[1] + s.K[r * 3 + 2] * P[2];
+            const bool act = KP[2] > 0.1;
+            const double zc = act ? KP[2] : 0.1, pr = KP[a2] / zc;
+            for (int k = 0; k < 3; ++k) {
+                const double coef = (s.K[a2 * 3 + k] - (act ? pr * s.K[6 + k] : 0.0)) / zc;
+                for (int m = 0; m < 6; ++m) r2[m] = fma(coef, s.rows[(3 * j + k) * 6 + m], r2[m]);
+            }
+        }
+        __syncthreads();
+        if (tid < 16)
+            for (int m = 0; m < 6; ++m) s.rows[tid * 6 + m] = r2[m];
+    }
     __syncthreads(); LC_MARK(1);
     if (tid == 0) {
         // safe_cholesky: non-SPD -> identity (pnp_utils.py:140-167)
@@ -429,7 +452,7 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
     __syncthreads(); LC_MARK(3);
     mm6_par<NT>(s.T1, s.C, s.M);  // M = C G C
     __syncthreads(); LC_MARK(4);
-    if (tid < 24) {
+    if (tid < 8 * nd) {
         const double* row = s.rows + tid * 6;
         double vc = 0.0, vm = 0.0, uu = 0.0;
         for (int r = 0; r < 6; ++r) {
@@ -443,13 +466,13 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
     // per-corner sums on 8 threads, then the scalar loss on one
     if (tid < 8) {
         const int j = tid;
-        s.wC[j] = s.vC[3 * j] + s.vC[3 * j + 1] + s.vC[3 * j + 2];
-        s.wM[j] = s.vM[3 * j] + s.vM[3 * j + 1] + s.vM[3 * j + 2];
-        s.wU[j] = sqrt(s.u[3 * j] * s.u[3 * j] + s.u[3 * j + 1] * s.u[3 * j + 1] + s.u[3 * j + 2] * s.u[3 * j + 2]);
+        double wc = 0.0, wm = 0.0, wu = 0.0;
+        for (int r = 0; r < nd; ++r) { wc += s.vC[nd * j + r]; wm += s.vM[nd * j + r]; wu = fma(s.u[nd * j + r], s.u[nd * j + r], wu); }
+        s.wC[j] = wc; s.wM[j] = wm; s.wU[j] = sqrt(wu);
     }
     if (tid == 32 % NT) {
         bool goodC = true, goodM = true;
-        for (int k = 0; k < 24; ++k) { goodC = goodC && (s.vC[k] > 0.0); goodM = goodM && (s.vM[k] > 0.0); }
+        for (int k = 0; k < 8 * nd; ++k) { goodC = goodC && (s.vC[k] > 0.0); goodM = goodM && (s.vM[k] > 0.0); }
         if (!goodC) s.flag |= LC_ST_PRIOR_NOT_GOOD;
         if (!goodM) s.flag |= LC_ST_COV_NOT_GOOD;
     }
@@ -496,22 +519,23 @@ __device__ __forceinline__ void lc_six_forward(const lc_args& a, PoseShared& s, 
 
 // Reverse 6x6 section: fills s.cHL, s.cGL, s.bL (left basis, symmetrised, off-diagonals doubled,
 // already scaled by grad_scale*grad_out).  Ends with a barrier.
+// nd = coordinates per bbox corner (3; 2 for cov_2d), as in lc_six_forward.
 template <int NT>
-__device__ __forceinline__ void lc_six_backward(PoseShared& s) {
+__device__ __forceinline__ void lc_six_backward(PoseShared& s, int nd = 3) {
     const int tid = threadIdx.x;
     for (int e = tid; e < 36; e += NT) {
         const int r = e / 6, c = e % 6;
         double cb = 0.0, mb = 0.0;
-        for (int k = 0; k < 24; ++k) {
+        for (int k = 0; k < 8 * nd; ++k) {
             const double qq = s.rows[k * 6 + r] * s.rows[k * 6 + c];
-            cb = fma(s.wC[k / 3], qq, cb);
-            mb = fma(s.wM[k / 3], qq, mb);
+            cb = fma(s.wC[k / nd], qq, cb);
+            mb = fma(s.wM[k / nd], qq, mb);
         }
         s.Cbar[e] = cb; s.Mbar[e] = mb;
     }
     if (tid < 6) {
         double v = 0.0;
-        for (int k = 0; k < 24; ++k) v = fma(s.wU[k / 3] * s.u[k], s.rows[k * 6 + tid], v);
+        for (int k = 0; k < 8 * nd; ++k) v = fma(s.wU[k / nd] * s.u[k], s.rows[k * 6 + tid], v);
         s.dthbar[tid] = v;
     }
     __syncthreads(); LC_MARK(10);

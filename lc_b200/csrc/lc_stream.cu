@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64) ? (1024 / NT / 2) : 1) lc_pose_
     lc_six_forward<T, NT>(a, s, b);
     const bool want_grads = a.g_pts3d.ptr || a.g_pts2d.ptr || a.g_weights.ptr;
     if (!want_grads) return;
-    lc_six_backward<NT>(s);
+    lc_six_backward<NT>(s, (a.flags & LC_FLAG_COV_2D) ? 2 : 3);
 
     // gradient slots of the padding beyond n_points (ragged batches): defined, zero
     for (int i = n + tid; i < a.N; i += NT) {

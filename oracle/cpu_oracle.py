@@ -55,8 +55,9 @@ def _f32(a):
 
 
 def lc_loss(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, max_err_len=32.0, rel_thresh=3.0, w_e_thresh=4.0,
-            want_jac=False, threads=None):
-    """fp64 LC loss forward + gradients (for d loss_b = 1).  Returns a dict of numpy arrays."""
+            want_jac=False, threads=None, cov_2d=False):
+    """fp64 LC loss forward + gradients (for d loss_b = 1).  Returns a dict of numpy arrays.
+    ``cov_2d``: the projected-bbox variant of cov_mixed.py:76-80, 91-97."""
     K, pose, X, x, s, v, bb = map(_f64, (K, pose, pts3d, pts2d, inv_std, valid, bbox_3d))
     B, N = X.shape[0], X.shape[1]
     threads = threads or os.cpu_count()
@@ -66,11 +67,11 @@ def lc_loss(K, pose, pts3d, pts2d, inv_std, valid, bbox_3d, max_err_len=32.0, re
     jac = np.zeros((B, 6, N, 2)) if want_jac else None
     scratch = np.zeros(threads * 8 * N)
     D, I = C.c_double, C.c_int
-    lib().lc_oracle_batch(
+    lib().lc_oracle_batch_ex(
         I(B), I(N), _p(K, D), _p(pose, D), _p(X, D), _p(x, D), _p(s, D), _p(v, D), _p(bb, D),
         D(max_err_len), D(rel_thresh), D(w_e_thresh), _p(out["loss"], D), _p(out["g_pts3d"], D),
         _p(out["g_pts2d"], D), _p(out["g_inv_std"], D), _p(jac, D), _p(out["cov"], D), _p(out["update_cov"], D),
-        _p(out["W"], D), _p(out["sigma"], D), _p(out["flags"], I), _p(scratch, D), I(threads))
+        _p(out["W"], D), _p(out["sigma"], D), _p(out["flags"], I), _p(scratch, D), I(threads), I(1 if cov_2d else 0))
     if want_jac:
         out["jac"] = jac
     return out

@@ -112,11 +112,11 @@ static void point_jac(const double K[9], const double R[9], const double t[3], c
 }
 
 /* rho(S) of SURVEY §8a: mean_j sqrt(good ? sum_xyz diag(Jb_j S Jb_j^T) : 1); also returns per-corner sums */
-static double rho_cov(const double Jb[8][18], const double S[36], double sj[8], int* good) {
+static double rho_cov(const double Jb[8][18], int nd, const double S[36], double sj[8], int* good) {
     *good = 1;
     for (int j = 0; j < 8; ++j) {
         sj[j] = 0;
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < nd; ++r) {
             const double* row = &Jb[j][r * 6];
             double v = 0;
             for (int a = 0; a < 6; ++a) {
@@ -139,10 +139,11 @@ static double rho_cov(const double Jb[8][18], const double S[36], double sj[8], 
  * A[6*N*2] = jac_pts2update, C[36] = prior_update_cov, M[36] = update_cov,
  * Wout[N*2], sig_out[N*2], flag[1] (bit0: Hessian not SPD -> identity; bit1: !good^C; bit2: !good^M).
  */
-void lc_oracle_pose(const double* K, const double* pose, const double* X, const double* x, const double* s,
-                    const double* valid, const double* bbox, int N, double Lmax, double rel, double we,
-                    double* loss, double* gX, double* gx, double* gs, double* A, double* C_out, double* M_out,
-                    double* Wout, double* sig_out, int* flag, double* scratch /* >= 8*N doubles */) {
+void lc_oracle_pose_ex(const double* K, const double* pose, const double* X, const double* x, const double* s,
+                       const double* valid, const double* bbox, int N, double Lmax, double rel, double we,
+                       double* loss, double* gX, double* gx, double* gs, double* A, double* C_out, double* M_out,
+                       double* Wout, double* sig_out, int* flag, double* scratch /* >= 8*N doubles */,
+                       int cov2d /* cov_mixed.py:76-80: corner covariances of the projected bbox instead of the 3-D one */) {
     double R[9];
     quat_to_R_ref(pose, R);
     const double* t = pose + 4;
@@ -259,16 +260,39 @@ void lc_oracle_pose(const double* K, const double* pose, const double* X, const 
             for (int cc = 0; cc < 3; ++cc) Jb[j][r * 6 + 3 + cc] = (r == cc) ? 1.0 : 0.0;
         }
     }
+    /* cov_2d (cov_mixed.py:76-80, 91-97, 129-131): the rows are those of the PROJECTED corners, xform_2d = project_apply(K, R c + t):
+     * row2d[j][a] = sum_k dproj_a/dP_k row3d[j][k],  dproj/dP = (K[:2,:] - proj (x) K[2,:] [z > 0.1]) / max(z, 0.1);  two per corner. */
+    const int nd = cov2d ? 2 : 3;
+    if (cov2d) {
+        for (int j = 0; j < 8; ++j) {
+            const double* c = bbox + 3 * j;
+            double P[3], KP[3], r3[18];
+            for (int r = 0; r < 3; ++r) P[r] = R[r * 3] * c[0] + R[r * 3 + 1] * c[1] + R[r * 3 + 2] * c[2] + t[r];
+            for (int r = 0; r < 3; ++r) KP[r] = K[r * 3] * P[0] + K[r * 3 + 1] * P[1] + K[r * 3 + 2] * P[2];
+            const int act = KP[2] > 0.1;   /* clamp(min=0.1): gradient passes where z >= min; equality has measure zero */
+            const double zc = act ? KP[2] : 0.1;
+            memcpy(r3, Jb[j], sizeof(r3));
+            for (int a2 = 0; a2 < 2; ++a2) {
+                const double pr = KP[a2] / zc;
+                for (int m = 0; m < 6; ++m) {
+                    double v = 0;
+                    for (int k = 0; k < 3; ++k) v += (K[a2 * 3 + k] - (act ? pr * K[6 + k] : 0.0)) / zc * r3[k * 6 + m];
+                    Jb[j][a2 * 6 + m] = v;
+                }
+            }
+            for (int m = 0; m < 6; ++m) Jb[j][12 + m] = 0.0;
+        }
+    }
     double sC[8], sM[8], un[8], u[8][3];
     int goodC, goodM;
-    const double prior = rho_cov(Jb, Cm, sC, &goodC);
-    const double cov_err = rho_cov(Jb, Mm, sM, &goodM);
+    const double prior = rho_cov(Jb, nd, Cm, sC, &goodC);
+    const double cov_err = rho_cov(Jb, nd, Mm, sM, &goodM);
     if (!goodC) fl |= 2;
     if (!goodM) fl |= 4;
     double lin = 0;
     for (int j = 0; j < 8; ++j) {
         double n2 = 0;
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < nd; ++r) {
             double v = 0;
             for (int a = 0; a < 6; ++a) v += Jb[j][r * 6 + a] * dth[a];
             u[j][r] = v; n2 += v * v;
@@ -288,7 +312,7 @@ void lc_oracle_pose(const double* K, const double* pose, const double* X, const 
     for (int j = 0; j < 8; ++j) {
         const double wc = goodC ? g_p / (16.0 * sqrt(sC[j])) : 0.0;
         const double wm = goodM ? g_c / (16.0 * sqrt(sM[j])) : 0.0;
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < nd; ++r)
             for (int a = 0; a < 6; ++a)
                 for (int b = 0; b < 6; ++b) {
                     const double qq = Jb[j][r * 6 + a] * Jb[j][r * 6 + b];
@@ -296,7 +320,7 @@ void lc_oracle_pose(const double* K, const double* pose, const double* X, const 
                     Mbar[a * 6 + b] += wm * qq;
                 }
         if (un[j] > 0)
-            for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < nd; ++r)
                 for (int a = 0; a < 6; ++a) dthbar[a] += g_c / 8.0 * Jb[j][r * 6 + a] * u[j][r] / un[j];
     }
     double Gbar[36], bbar[6], Hbar[36], T2[36];
@@ -351,11 +375,18 @@ void lc_oracle_pose(const double* K, const double* pose, const double* X, const 
     }
 }
 
+void lc_oracle_pose(const double* K, const double* pose, const double* X, const double* x, const double* s,
+                    const double* valid, const double* bbox, int N, double Lmax, double rel, double we,
+                    double* loss, double* gX, double* gx, double* gs, double* A, double* C_out, double* M_out,
+                    double* Wout, double* sig_out, int* flag, double* scratch) {
+    lc_oracle_pose_ex(K, pose, X, x, s, valid, bbox, N, Lmax, rel, we, loss, gX, gx, gs, A, C_out, M_out, Wout, sig_out, flag, scratch, 0);
+}
+
 /* Batch driver: contiguous AoS fp64 arrays; OpenMP over poses (mirrors ceres.cpp:161-169 threading). */
-void lc_oracle_batch(int B, int N, const double* K, const double* pose, const double* X, const double* x,
-                     const double* s, const double* valid, const double* bbox, double Lmax, double rel, double we,
-                     double* loss, double* gX, double* gx, double* gs, double* A, double* C, double* M,
-                     double* W, double* sig, int* flags, double* scratch /* threads*8*N */, int threads) {
+void lc_oracle_batch_ex(int B, int N, const double* K, const double* pose, const double* X, const double* x,
+                        const double* s, const double* valid, const double* bbox, double Lmax, double rel, double we,
+                        double* loss, double* gX, double* gx, double* gs, double* A, double* C, double* M,
+                        double* W, double* sig, int* flags, double* scratch /* threads*8*N */, int threads, int cov2d) {
     if (threads < 1) threads = 1;
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
@@ -365,11 +396,18 @@ void lc_oracle_batch(int B, int N, const double* K, const double* pose, const do
         const int tid = 0;
 #endif
         const size_t n = (size_t)N;
-        lc_oracle_pose(K + 9 * b, pose + 7 * b, X + 3 * n * b, x + 2 * n * b, s + 2 * n * b,
+        lc_oracle_pose_ex(K + 9 * b, pose + 7 * b, X + 3 * n * b, x + 2 * n * b, s + 2 * n * b,
                        valid ? valid + n * b : NULL, bbox + 24 * b, N, Lmax, rel, we,
                        loss ? loss + b : NULL, gX ? gX + 3 * n * b : NULL, gx ? gx + 2 * n * b : NULL,
                        gs ? gs + 2 * n * b : NULL, A ? A + 12 * n * b : NULL, C ? C + 36 * b : NULL,
                        M ? M + 36 * b : NULL, W ? W + 2 * n * b : NULL, sig ? sig + 2 * n * b : NULL,
-                       flags ? flags + b : NULL, scratch + (size_t)tid * 8 * n);
+                       flags ? flags + b : NULL, scratch + (size_t)tid * 8 * n, cov2d);
     }
+}
+
+void lc_oracle_batch(int B, int N, const double* K, const double* pose, const double* X, const double* x,
+                     const double* s, const double* valid, const double* bbox, double Lmax, double rel, double we,
+                     double* loss, double* gX, double* gx, double* gs, double* A, double* C, double* M,
+                     double* W, double* sig, int* flags, double* scratch, int threads) {
+    lc_oracle_batch_ex(B, N, K, pose, X, x, s, valid, bbox, Lmax, rel, we, loss, gX, gx, gs, A, C, M, W, sig, flags, scratch, threads, 0);
 }

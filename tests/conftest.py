@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 
 def golden_files():
-    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("jacx_", "densex_", "zebra_", "select_", "eval_", "init_")))
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("jacx_", "densex_", "zebra_", "select_", "eval_", "init_", "cov2d_")))
 
 
 def load_golden(name):

@@ -87,6 +87,26 @@ def run_reference(d, max_err_len=32, rel_thresh=3, w_e_thresh=4):
                 jac=jac.detach(), cov=cov.detach())
 
 
+def make_cov2d():
+    """Loss_cov_mixed(..., cov_2d=True) (cov_mixed.py:76-80, 91-97, 129-131): the projected-bbox-corner variant no reference config
+    enables.  Stand-alone fixtures so the files of the default variant stay untouched."""
+    for name, B, N, seed, vm in (("cov2d_b3_n200_s4", 3, 200, 4, "ones"), ("cov2d_b2_n16_s5", 2, 16, 5, "none"), ("cov2d_b2_n700_s6_mask", 2, 700, 6, "mask")):
+        d = build_inputs(B, N, seed, vm, "nominal")
+        pts3d = d["pts3d"].clone().requires_grad_(True)
+        pts2d = d["pts2d"].clone().requires_grad_(True)
+        inv_std = d["inv_std"].clone().requires_grad_(True)
+        loss = Loss_cov_mixed(d["K"], d["pose"], pts3d, pts2d, inv_std, d["valid"], bbox_3d=d["bbox_3d"], max_err_len=32, cov_2d=True)
+        g3, g2, gs = torch.autograd.grad(loss.sum(), (pts3d, pts2d, inv_std))
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, in_K=d["K"].numpy().astype(np.float32), in_pose=d["pose"].numpy().astype(np.float32),
+                            in_pts3d=d["pts3d"].numpy().astype(np.float32), in_pts2d=d["pts2d"].numpy().astype(np.float32),
+                            in_inv_std=d["inv_std"].numpy().astype(np.float32), in_bbox_3d=d["bbox_3d"].numpy().astype(np.float32),
+                            has_valid=np.array(d["valid"] is not None),
+                            in_valid=(d["valid"].numpy().astype(np.float32) if d["valid"] is not None else np.zeros((B, N), np.float32)),
+                            ref_loss=loss.detach().numpy(), ref_g_pts3d=g3.numpy(), ref_g_pts2d=g2.numpy(), ref_g_inv_std=gs.numpy())
+        print(name, os.path.getsize(path) // 1024, "KiB", loss.detach().numpy())
+
+
 def make_jac_exact():
     """weighted_pnp_jac_wrt_pts2d AWAY from the optimum (measured pts2d, residual != 0): exercises the r * d2r term
     of hessian_6d_elem (pnp_auto.py:59-83) and the double-backward w.r.t. the weights (:129-134)."""
@@ -313,6 +333,9 @@ def make_init():
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if "--only-cov2d" in sys.argv:
+        make_cov2d()
+        return
     if "--only-init" in sys.argv:
         make_init()
         return
@@ -326,6 +349,7 @@ def main():
         make_select()
         return
     make_jac_exact()
+    make_cov2d()
     make_dense()
     make_zebra()
     make_select()

@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_files, load_golden, rel_err
+import os
+
+from conftest import GOLDEN_DIR, golden_files, load_golden, rel_err
 from lc_b200.synth import make_correspondences, planar_view
 
 pytestmark = pytest.mark.gpu
@@ -315,3 +317,35 @@ def test_repeated_launches_are_bit_identical(B, N, planar):
             first = cur
         else:
             assert all(torch.equal(p, q) for p, q in zip(first, cur))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("name", ["cov2d_b3_n200_s4.npz", "cov2d_b2_n16_s5.npz", "cov2d_b2_n700_s6_mask.npz"])
+def test_cov_2d_variant_matches_the_reference(name, dtype):
+    """Loss_cov_mixed(..., cov_2d=True): corner covariances of the projected bbox (lib/cov_mixed.py:76-80, 91-97) against fixtures
+    from the unmodified reference, through the drop-in autograd operator (fp32 like the reference runs, fp64 for the math)."""
+    from lc_b200.cov_mixed import Loss_cov_mixed
+    from lc_b200 import _native as nat
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    t = lambda k: torch.as_tensor(z[k]).to(device="cuda", dtype=dtype)
+    p3, p2, s = t("in_pts3d").requires_grad_(True), t("in_pts2d").requires_grad_(True), t("in_inv_std").requires_grad_(True)
+    v = t("in_valid") if bool(z["has_valid"]) else None
+    loss = Loss_cov_mixed(t("in_K"), t("in_pose"), p3, p2, s, v, bbox_3d=t("in_bbox_3d"), max_err_len=32, cov_2d=True)
+    assert b"lc_pose_kernel" in nat.lib().lc_b200_last_kernels()
+    loss.sum().backward()
+    # fp64: bounded by the non-unit-quaternion deviation of the left-basis trick (DESIGN.md 7: ~| |q| - 1 | of an fp32-rounded pose)
+    tol_l, tol_g = (2e-5, 2e-4) if dtype == torch.float32 else (5e-7, 5e-6)
+    assert np.abs(loss.detach().cpu().numpy() - z["ref_loss"]).max() <= tol_l * np.abs(z["ref_loss"]).max()
+    for g, k in ((p3.grad, "ref_g_pts3d"), (p2.grad, "ref_g_pts2d"), (s.grad, "ref_g_inv_std")):
+        assert rel_err(g.cpu().numpy(), z[k]) <= tol_g, k
+
+
+def test_cov_2d_is_rejected_by_the_fused_entry_point():
+    from lc_b200 import _native as nat
+    from lc_b200.synth import make_correspondences
+    c = make_correspondences(2, 100, 1).to(torch.float32).to(device="cuda")
+    st = torch.empty(2, 7, device="cuda"); loss = torch.empty(2, device="cuda")
+    a = nat.make_args(2, 100, torch.float32, K=c.K, pose=c.start, pts3d=c.pts3d, pts2d=c.pts2d, weights=c.inv_std, bbox=c.bbox_3d,
+                      state=st, loss=loss, weight_mode=nat.W_INV_STD, flags=nat.FLAG_COV_2D)
+    with pytest.raises(Exception):
+        nat.call("lc_b200_solve_loss", a, c.K.device)

@@ -3,7 +3,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_files, load_golden, rel_err, quat_angle
+import os
+
+from conftest import GOLDEN_DIR, golden_files, load_golden, rel_err, quat_angle
 from lc_b200.synth import make_correspondences, quat_to_matrix
 
 
@@ -274,3 +276,17 @@ def test_lm_oracle_rule_switches_are_wired(oracle):
     assert (again["iters"] == 2).all() and (unguarded["iters"] == 1).all()
     # candidate discarded: the start comes back (through quaternion -> angle-axis -> quaternion in fp32)
     assert np.allclose(unguarded["states"], base["states"], rtol=3e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["cov2d_b3_n200_s4.npz", "cov2d_b2_n16_s5.npz", "cov2d_b2_n700_s6_mask.npz"])
+def test_oracle_cov_2d_matches_the_reference(oracle, name):
+    """Loss_cov_mixed(..., cov_2d=True) (lib/cov_mixed.py:76-80, 91-97): fixtures generated by the unmodified reference
+    (tests/golden/make_golden.py --only-cov2d)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    v = z["in_valid"] if bool(z["has_valid"]) else None
+    o = oracle.lc_loss(z["in_K"], z["in_pose"], z["in_pts3d"], z["in_pts2d"], z["in_inv_std"], v, z["in_bbox_3d"], cov_2d=True)
+    assert np.abs(o["loss"] - z["ref_loss"]).max() <= 1e-12 * np.abs(z["ref_loss"]).max()
+    for k in ("g_pts3d", "g_pts2d", "g_inv_std"):
+        assert np.abs(o[k] - z["ref_" + k]).max() <= 1e-11 * np.abs(z["ref_" + k]).max(), k
+    o3 = oracle.lc_loss(z["in_K"], z["in_pose"], z["in_pts3d"], z["in_pts2d"], z["in_inv_std"], v, z["in_bbox_3d"])
+    assert np.abs(o3["loss"] - z["ref_loss"]).max() > 0.1   # the 3-D variant is a different loss
