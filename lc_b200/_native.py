@@ -17,7 +17,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("LC_B200_LIB") or os.path.join(_HERE, "liblc_b200.so")   # env override: instrumented builds (tools/)
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_resident_vec.cu", "lc_resident_cluster.cu", "lc_persist.cu", "lc_tiny.cu", "lc_dense.cu", "lc_select.cu", "lc_eval.cu", "lc_init.cu", "lc_compat.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("lc_abi.cu", "lc_stream.cu", "lc_resident.cu", "lc_resident_vec.cu", "lc_resident_cluster.cu", "lc_resident_lm3.cu", "lc_persist.cu", "lc_tiny.cu", "lc_dense.cu", "lc_select.cu", "lc_eval.cu", "lc_init.cu", "lc_compat.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "lc_device.cuh"), os.path.join(_HERE, "csrc", "lc_pose.cuh"),
            os.path.join(_HERE, "csrc", "lc_resident.cuh"), os.path.join(_HERE, "csrc", "lc_vec.cuh"),
            os.path.join(_HERE, "csrc", "lc_resident_kernel.cuh"), os.path.join(_HERE, "csrc", "lc_point.cuh"),

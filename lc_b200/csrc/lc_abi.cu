@@ -61,6 +61,8 @@ static int dispatch_pose(const lc_args* a, int mode, void* stream) {
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && a->N <= kTinyMaxN) return check_launch(launch_tiny_pose(*a, mode, st));
     // large N, many poses, planar slabs: the persistent pipelined kernel (one CTA per SM, two poses in flight, lc_persist.cu)
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && persist_supported(*a, mode)) return check_launch(launch_persist_pose(*a, mode, st));
+    // solve only, 2048 < N <= ~5.2k: three poses per SM (model points in shared memory, image points and weights streamed from L2)
+    if (!(a->flags & LC_FLAG_FORCE_STREAMING) && mode == MODE_LM && lm3_supported(*a)) return check_launch(launch_lm3(*a, st));
     if (!(a->flags & LC_FLAG_FORCE_STREAMING) && resident_supported(*a, mode)) return check_launch(launch_resident_pose(*a, mode, st));
     if (!(a->flags & LC_FLAG_FORCE_STREAMING)) {
         // Ragged batch padded beyond the resident limit (the test-time chain pads to the full map, test.py:106-119): poses with

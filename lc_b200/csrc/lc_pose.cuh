@@ -1067,6 +1067,8 @@ int launch_stream_jac(const lc_args& a, bool bwd, cudaStream_t st);
 bool resident_supported(const lc_args& a, int mode);
 int launch_resident_pose(const lc_args& a, int mode, cudaStream_t st, int cap = 0);
 int resident_split_capacity(const lc_args& a, int mode);
+bool lm3_supported(const lc_args& a);            // solve-only, three poses per SM (lc_resident_lm3.cu)
+int launch_lm3(const lc_args& a, cudaStream_t st);
 bool persist_supported(const lc_args& a, int mode);
 int launch_persist_pose(const lc_args& a, int mode, cudaStream_t st);
 int launch_tiny_pose(const lc_args& a, int mode, cudaStream_t st);

@@ -146,3 +146,33 @@ def test_mixed_precision_pass_keeps_the_schedule(oracle):
     assert np.array_equal(np.isnan(tg), np.isnan(tr))
     assert np.array_equal(tg[m].reshape(-1, 4)[:, 2], tr[m].reshape(-1, 4)[:, 2])            # accept / reject sequence
     assert np.allclose(tg[m].reshape(-1, 4)[:, :2], tr[m].reshape(-1, 4)[:, :2], rtol=1e-5)  # cost, radius
+
+
+@pytest.mark.parametrize("B,N,planar,seed", [(5, 4096, True, 3), (4, 2501, False, 4), (3, 3000, True, 5)])
+def test_three_poses_per_sm_solver_matches_the_oracle(oracle, monkeypatch, B, N, planar, seed):
+    """lc_lm3_kernel (lc_resident_lm3.cu: model points in shared memory, image points and weights streamed from L2, three CTAs per
+    SM; the default from B = 2048 on) forced at a small batch: states, iteration counts, invalid flags and radii vs the CPU LM
+    oracle, ragged n_points and the nan filter included; equal to the two-CTA kernel's result bit for bit (same arithmetic)."""
+    from lc_b200.pnp.cer_solver import lm_solve
+    from lc_b200 import _native as nat
+    from lc_b200.synth import planar_view
+    c = make_correspondences(B, N, seed).to(torch.float32)
+    npts = torch.tensor([N, N - 7, 2200, N, N][:B], dtype=torch.int32)
+    L = torch.diag_embed(c.inv_std)
+    ref = oracle.lm_solve(c.K, c.pts3d, c.pts2d, L, c.start, n_points=npts.numpy())
+    d = c.to(device="cuda")
+    X, x, w = (planar_view(d.pts3d), planar_view(d.pts2d), planar_view(d.inv_std)) if planar else (d.pts3d, d.pts2d, d.inv_std)
+    monkeypatch.setenv("LC_B200_LM3", "1")
+    o = lm_solve(d.K, X, x, w, d.start, npts.cuda(), weight_mode=nat.W_INV_STD, filter_input_nan=True)
+    torch.cuda.synchronize()
+    assert b"lc_lm3_kernel" in nat.lib().lc_b200_last_kernels()
+    monkeypatch.setenv("LC_B200_LM3", "0")
+    o2 = lm_solve(d.K, X, x, w, d.start, npts.cuda(), weight_mode=nat.W_INV_STD, filter_input_nan=True)
+    torch.cuda.synchronize()
+    assert b"lc_lm3_kernel" not in nat.lib().lc_b200_last_kernels()
+    assert np.array_equal(o["invalid"].cpu().numpy(), ref["invalid"]) and np.array_equal(o["iters"].cpu().numpy(), ref["iters"])
+    st = o["states"].cpu().numpy().astype(np.float64)
+    assert quat_angle(st[:, :4], ref["states"][:, :4].astype(np.float64)).max() <= 1e-6
+    assert (np.linalg.norm(st[:, 4:] - ref["states"][:, 4:], axis=1) / np.linalg.norm(ref["states"][:, 4:], axis=1)).max() <= 1e-6
+    assert np.allclose(o["radius"].cpu().numpy(), ref["radius"], rtol=1e-5)
+    assert torch.equal(o["iters"], o2["iters"]) and (o["states"] - o2["states"]).abs().max().item() <= 1e-6
