@@ -121,14 +121,40 @@ __global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_ar
     __shared__ int cnts[kSelMaxRounds * NW + 32];   // per (round, warp) selected counts -> exclusive offsets; [R * NW] = total
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // ---- segmentation threshold in logit space.  test.py:70 tests sigmoid(logit) > seg_thresh per pixel; the sigmoid evaluated here
+    //      (sel_sigmoid, which reproduces torch's mask bit for bit on the reference fixtures) is monotone, so the smallest float x*
+    //      with sel_sigmoid(x*) > seg_thresh is found once per sample by bisection over the ordered float bit patterns (one thread,
+    //      32 steps) and every pixel then costs one comparison instead of an exponential and a division. ----
+    __shared__ float s_xstar;
+    if (tid == 0) {
+        auto key2f = [](unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); };   // increasing key -> increasing float
+        const unsigned kmin = ~0xFF800000u /* -inf */, kmax = 0x7F800000u ^ 0x80000000u /* +inf */;
+        float xs;
+        if (!(sel_sigmoid(key2f(kmax)) > d.seg_thresh)) xs = NAN;              // nothing passes (comparisons with NaN are false)
+        else if (sel_sigmoid(key2f(kmin)) > d.seg_thresh) xs = -INFINITY;       // everything (finite or infinite) passes
+        else {
+            unsigned lo = kmin, hi = kmax;                                      // f(lo) fails, f(hi) passes
+            while (hi - lo > 1u) {
+                const unsigned mid = lo + ((hi - lo) >> 1);
+                if (sel_sigmoid(key2f(mid)) > d.seg_thresh) hi = mid; else lo = mid;
+            }
+            xs = key2f(hi);
+        }
+        s_xstar = xs;
+    }
     // ---- softmax statistics (test.py:84-88): joint over 2*H*W for a (B,1,1,1) scale, per channel for (B,2,1,1) ----
     const bool fused = d.weights.ptr == nullptr;
     const float* lg = fused ? static_cast<const float*>(d.logits.ptr) + b * d.logits.stride[0] : nullptr;
     const int64_t lgc = fused ? d.logits.stride[1] : 0;
+    const float* ml = static_cast<const float*>(d.msk_logits.ptr) + b * d.msk_logits.stride[0];
+    // both logit planes are contiguous (lc_abi.cu checks): 16-byte loads when the planes are 16-byte aligned
+    const bool v4 = fused && (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0 && (lgc & 3) == 0;
+    const bool ml_lin = d.sample == 1 && d.msk_logits.stride[2] == 1 && d.msk_logits.stride[1] == d.W;
+    // every pixel sampled, joint softmax, everything contiguous: the sum pass also produces the per-pixel operands (below)
+    const bool merged = v4 && ml_lin && d.scale_dim == 1 && (reinterpret_cast<uintptr_t>(ml) & 15) == 0;
     float m0 = 0.f, m1 = 0.f, k0 = 1.f, k1 = 1.f;
+    int cnt = 0;
     if (fused) {
-        // both planes are contiguous (lc_abi.cu checks): 16-byte loads when the planes are 16-byte aligned
-        const bool v4 = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0 && (lgc & 3) == 0;
         float mx0 = -INFINITY, mx1 = -INFINITY;
         if (v4) {
             const float4* p0 = reinterpret_cast<const float4*>(lg);
@@ -153,7 +179,30 @@ __global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_ar
         __syncthreads();
         m0 = sm_stat[0]; m1 = sm_stat[1];
         float s0 = 0.f, s1 = 0.f;
-        if (v4) {
+        if (merged) {
+            // one pass: exponentials once per pixel -> their sums AND the quantile operand e0 + e1 (UNNORMALISED: the order statistic,
+            // the interpolated threshold and every comparison are invariant to the common positive factor scale / Z up to the
+            // rounding the fused mode tolerates anyway) and the mask flag, four pixels per thread and trip
+            const float xstar = s_xstar;
+            const float4* p0 = reinterpret_cast<const float4*>(lg);
+            const float4* p1 = reinterpret_cast<const float4*>(lg + lgc);
+            const float4* pm = reinterpret_cast<const float4*>(ml);
+            const bool qim = d.mode == LC_SEL_QUANTILE_IN_MASK;
+            for (int j = tid; j < (HW >> 2); j += kSelNT) {
+                const float4 a = __ldg(p0 + j), c = __ldg(p1 + j), q = __ldg(pm + j);
+                const float e0x = expf(a.x - m0), e0y = expf(a.y - m0), e0z = expf(a.z - m0), e0w = expf(a.w - m0);
+                const float e1x = expf(c.x - m1), e1y = expf(c.y - m1), e1z = expf(c.z - m1), e1w = expf(c.w - m1);
+                s0 += (e0x + e0y) + (e0z + e0w);
+                s1 += (e1x + e1y) + (e1z + e1w);
+                const bool mx = q.x >= xstar, my = q.y >= xstar, mz = q.z >= xstar, mw = q.w >= xstar;
+                float4 v;
+                v.x = (!qim || mx) ? __fadd_rn(e0x, e1x) : 0.f; v.y = (!qim || my) ? __fadd_rn(e0y, e1y) : 0.f;
+                v.z = (!qim || mz) ? __fadd_rn(e0z, e1z) : 0.f; v.w = (!qim || mw) ? __fadd_rn(e0w, e1w) : 0.f;
+                *reinterpret_cast<float4*>(vals + 4 * j) = v;
+                *reinterpret_cast<unsigned*>(mflag + 4 * j) = (mx ? 1u : 0u) | (my ? 0x100u : 0u) | (mz ? 0x10000u : 0u) | (mw ? 0x1000000u : 0u);
+                cnt += (mx ? 1 : 0) + (my ? 1 : 0) + (mz ? 1 : 0) + (mw ? 1 : 0);
+            }
+        } else if (v4) {
             const float4* p0 = reinterpret_cast<const float4*>(lg);
             const float4* p1 = reinterpret_cast<const float4*>(lg + lgc);
             for (int j = tid; j < (HW >> 2); j += kSelNT) {
@@ -178,28 +227,31 @@ __global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_ar
         }
         __syncthreads();
         k0 = sm_stat[2]; k1 = sm_stat[3];
+    } else {
+        __syncthreads();   // s_xstar
     }
+    const float xstar = s_xstar;
     const float* wp = fused ? nullptr : static_cast<const float*>(d.weights.ptr) + b * d.weights.stride[0];
     const int64_t wpc = fused ? 0 : d.weights.stride[1], wpy = fused ? 0 : d.weights.stride[2], wpx = fused ? 0 : d.weights.stride[3];
     auto inv_std_at = [&](int y, int x, float& w0, float& w1) {
         if (fused) { const int p = y * d.W + x; w0 = expf(lg[p] - m0) * k0; w1 = expf(lg[lgc + p] - m1) * k1; }
         else { const int64_t o = y * wpy + x * wpx; w0 = wp[o]; w1 = wp[o + wpc]; }
     };
-    const float* ml = static_cast<const float*>(d.msk_logits.ptr) + b * d.msk_logits.stride[0];
 
     // ---- per sampled pixel: segmentation flag and the quantile operand ----
-    int cnt = 0;
+    if (!merged) {
 #pragma unroll 4
-    for (int i = tid; i < N; i += kSelNT) {
-        const int yq = i / Wn, xq = i - yq * Wn, y = yq * d.sample, x = xq * d.sample;
-        const bool m = sel_sigmoid(ml[y * d.msk_logits.stride[1] + x * d.msk_logits.stride[2]]) > d.seg_thresh;   // test.py:70
-        float w0, w1;
-        inv_std_at(y, x, w0, w1);
-        const float mf = m ? 1.f : 0.f;
-        // quantile_msk: weights = den_inv_std2d.sum(-1)  (of inv_std * mask for 'quantile_in_mask', test.py:104)
-        vals[i] = d.mode == LC_SEL_QUANTILE_IN_MASK ? __fadd_rn(__fmul_rn(w0, mf), __fmul_rn(w1, mf)) : __fadd_rn(w0, w1);
-        mflag[i] = m ? 1 : 0;
-        cnt += m ? 1 : 0;
+        for (int i = tid; i < N; i += kSelNT) {
+            const int yq = i / Wn, xq = i - yq * Wn, y = yq * d.sample, x = xq * d.sample;
+            const bool m = (ml_lin ? ml[i] : ml[y * d.msk_logits.stride[1] + x * d.msk_logits.stride[2]]) >= xstar;   // test.py:70
+            float w0, w1;
+            inv_std_at(y, x, w0, w1);
+            const float mf = m ? 1.f : 0.f;
+            // quantile_msk: weights = den_inv_std2d.sum(-1)  (of inv_std * mask for 'quantile_in_mask', test.py:104)
+            vals[i] = d.mode == LC_SEL_QUANTILE_IN_MASK ? __fadd_rn(__fmul_rn(w0, mf), __fmul_rn(w1, mf)) : __fadd_rn(w0, w1);
+            mflag[i] = m ? 1 : 0;
+            cnt += m ? 1 : 0;
+        }
     }
     cnt = __reduce_add_sync(kFull, cnt);
     if (lane == 0) wsum[warp] = cnt;
