@@ -63,5 +63,21 @@ solve_and_loss(c.K, c.start, X, x, w, None, c.bbox_3d, need=(True, True, True))
 lm_solve(c.K, X, x, w, c.start, weight_mode=nat.W_INV_STD)
 assert b"persist" in nat.lib().lc_b200_last_kernels()
 del os.environ["LC_B200_PERSIST"]
+# round 2 paths: poses split over two-CTA clusters (DSMEM reduction exchange, PDL-chained launches), the solve-only kernel with three
+# poses per SM, the cov_2d variant of the loss
+for env, val in (("LC_B200_SPLIT", "1"), ("LC_B200_LM3", "1")):
+    os.environ[env] = val
+    c = make_correspondences(5, 2048, 4).to(torch.float32).to(device="cuda")
+    c2 = make_correspondences(3, 2504, 5).to(torch.float32).to(device="cuda")
+    for cc in (c, c2):
+        X, x, w = planar_view(cc.pts3d), planar_view(cc.pts2d), planar_view(cc.inv_std)
+        npts = torch.tensor([cc.pts3d.shape[1], 900, 1500, 2000, 2048][: cc.pts3d.shape[0]], dtype=torch.int32, device="cuda")
+        loss_fwd_bwd(cc.K, cc.pose, X, x, w, None, cc.bbox_3d, n_points=npts)
+        solve_and_loss(cc.K, cc.start, X, x, w, None, cc.bbox_3d, need=(True, True, True), n_points=npts)
+        lm_solve(cc.K, X, x, w, cc.start, npts, weight_mode=nat.W_INV_STD, filter_input_nan=True)
+        lm_solve(cc.K, cc.pts3d, cc.pts2d, cc.inv_std, cc.start, weight_mode=nat.W_INV_STD)
+    del os.environ[env]
+c = make_correspondences(3, 200, 6).to(torch.float32).to(device="cuda")
+loss_fwd_bwd(c.K, c.pose, c.pts3d, c.pts2d, c.inv_std, c.valid, c.bbox_3d, cov_2d=True)
 torch.cuda.synchronize()
 print("sanitize smoke done")
