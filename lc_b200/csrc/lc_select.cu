@@ -42,8 +42,12 @@ __device__ void radix_select_pair(const unsigned* u, int n, int k, unsigned* his
             const unsigned v = i < n ? u[i] : 0u;
             const bool act = i < n && (v & mask) == prefix;
             const unsigned key = act ? ((v >> sh) & 255u) : 0xFFFFu;
-            const unsigned peers = __match_any_sync(kFull, key);
-            if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[key], static_cast<unsigned>(__popc(peers)));
+            if (pass >= 2) {   // leading bytes: a few bins take everything -> aggregate the lanes of a bin first
+                const unsigned peers = __match_any_sync(kFull, key);
+                if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[key], static_cast<unsigned>(__popc(peers)));
+            } else if (act) {  // trailing bytes are spread evenly: plain atomics
+                atomicAdd(&hist[key], 1u);
+            }
         }
         __syncthreads();
         if (tid < 32) {
@@ -304,12 +308,23 @@ __global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_ar
         stf(d.inv_cov, oc, w0 * w0); stf(d.inv_cov, oc + d.inv_cov.stride[2], w1 * w1);
         if (d.index) d.index[static_cast<int64_t>(b) * d.Nmax + slot] = i;
     };
-    // counts of every (round, warp) cell first, one scan over them, then every thread knows its output slot: three barriers in
-    // total instead of three per round of 1024 pixels
+    // Compaction in four steps, three barriers: (1) every thread evaluates its pixels once, keeps the verdicts as a bit mask in
+    // registers and the counts of all (round, warp) cells go to shared memory; (2) one warp scans the cells; (3) the indices of
+    // the selected pixels are written, in order, into the operand array (nobody reads the operands any more); (4) a DENSE loop
+    // over the output slots gathers and writes: every lane busy, consecutive lanes -> consecutive output rows (the selection keeps
+    // about a quarter of the pixels, so emitting from the pixel loop ran with a quarter of the lanes and a load latency per round).
     const int R = (N + kSelNT - 1) / kSelNT;
-    for (int r = 0; r < R; ++r) {
-        const unsigned bal = __ballot_sync(kFull, keep(r * kSelNT + tid));
-        if (lane == 0) cnts[r * NW + warp] = __popc(bal);
+    unsigned kept[(kSelMaxRounds + 31) / 32];
+#pragma unroll
+    for (int w = 0; w < (kSelMaxRounds + 31) / 32; ++w) kept[w] = 0u;
+#pragma unroll
+    for (int w = 0; w < (kSelMaxRounds + 31) / 32; ++w) {
+        for (int r = 32 * w; r < min(R, 32 * w + 32); ++r) {
+            const bool v = keep(r * kSelNT + tid);
+            const unsigned bal = __ballot_sync(kFull, v);
+            if (v) kept[w] |= 1u << (r & 31);
+            if (lane == 0) cnts[r * NW + warp] = __popc(bal);
+        }
     }
     __syncthreads();
     if (tid < 32) {
@@ -326,12 +341,20 @@ __global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_ar
         if (lane == 0) cnts[cells] = carry;
     }
     __syncthreads();
+    int* sel = reinterpret_cast<int*>(vals);   // slot -> pixel index (slot <= index: the list fits where the operands were)
+#pragma unroll
+    for (int w = 0; w < (kSelMaxRounds + 31) / 32; ++w) {
+        for (int r = 32 * w; r < min(R, 32 * w + 32); ++r) {
+            const bool v = (kept[w] >> (r & 31)) & 1u;
+            const unsigned bal = __ballot_sync(kFull, v);
+            if (v) sel[cnts[r * NW + warp] + __popc(bal & ((1u << lane) - 1u))] = r * kSelNT + tid;
+        }
+    }
+    __syncthreads();
+    {
+        const int nsel = cnts[R * NW];
 #pragma unroll 2
-    for (int r = 0; r < R; ++r) {
-        const int i = r * kSelNT + tid;
-        const bool v = keep(i);
-        const unsigned bal = __ballot_sync(kFull, v);
-        if (v) emit(cnts[r * NW + warp] + __popc(bal & ((1u << lane) - 1u)), i);
+        for (int slot = tid; slot < nsel; slot += kSelNT) emit(slot, sel[slot]);
     }
     int total = cnts[R * NW];
     // fewer than min_points selected: pad with indices drawn from all N points (test.py:108-113 uses np.random.choice; here a
