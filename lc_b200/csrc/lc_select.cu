@@ -7,8 +7,8 @@
 // -> ONE launch, one CTA per sample, that writes zero-padded (B,Nmax,.) correspondences in selection order plus n_points:
 // exactly what cer_solver._batch_tensors (cer_solver.py:67-87) would build, without the device->host sync of nonzero().
 //
-// The per-sample quantile is an exact order statistic: 4-pass 8-bit radix select over the fp32 bit patterns held in
-// shared memory (values are >= 0, so the bit patterns are ordered), followed by torch's fp32 lerp.
+// The per-sample quantile is an exact order statistic: a radix select over the fp32 bit patterns held in
+// shared memory (values are >= 0, so the bit patterns are ordered; round 2: three passes of 11 + 11 + 10 bits), followed by torch's fp32 lerp.
 //
 // Round 2: the same one-CTA-per-sample structure with its serial pieces removed — warp-aggregated histogram atomics (the keys of a
 // sample share their leading byte, plain atomics serialised 32-way), warp-scan bin search, one scan over all (round, warp) cells
@@ -26,56 +26,62 @@ constexpr int kSelNT = 512;
 __device__ __forceinline__ float sel_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 // value of the rank-k (0-based) smallest key among u[0..n) and of its successor in sorted order; all threads call.
-// Four 8-bit passes.  The keys of one sample share their leading bits (similar magnitudes), so a plain shared-memory atomicAdd
-// per key serialises on a handful of bins: the lanes of a warp that hit the same bin are aggregated with match.any first (one
-// atomic per distinct bin and warp).  The bin scan is a warp scan over 32 x 8 bins instead of one thread walking 256 counters.
+// Three radix passes over the 32 bits of the pattern (11 + 11 + 10).  The keys of one sample share their leading
+// bits (similar magnitudes), so in the FIRST pass a plain shared-memory atomicAdd per key would serialise on a handful of bins:
+// the lanes of a warp that hit the same bin are aggregated with match.any (one atomic per distinct bin and warp); the trailing
+// bits are spread evenly and take plain atomics.  The bin search is a warp scan (64 bins per lane), not one thread walking them.
+constexpr int kSelBins = 2048;
 __device__ void radix_select_pair(const unsigned* u, int n, int k, unsigned* hist, unsigned* bc, unsigned& kth, unsigned& next) {
     const int tid = threadIdx.x, lane = tid & 31;
     unsigned prefix = 0, mask = 0;
     int kk = k;
-    for (int j = tid; j < 256; j += kSelNT) hist[j] = 0;
+    for (int j = tid; j < kSelBins; j += kSelNT) hist[j] = 0;
     __syncthreads();
     const int n_up = (n + 31) & ~31;   // warp-uniform trip count (match.any is warp-collective)
-    for (int pass = 3; pass >= 0; --pass) {
-        const int sh = 8 * pass;
-        for (int i = tid; i < n_up; i += kSelNT) {
-            const unsigned v = i < n ? u[i] : 0u;
-            const bool act = i < n && (v & mask) == prefix;
-            const unsigned key = act ? ((v >> sh) & 255u) : 0xFFFFu;
-            if (pass >= 2) {   // leading bytes: a few bins take everything -> aggregate the lanes of a bin first
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        const int sh = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const unsigned bm = pass == 2 ? 1023u : 2047u;
+        if (pass == 0) {
+            for (int i = tid; i < n_up; i += kSelNT) {
+                const bool act = i < n;
+                const unsigned key = act ? ((u[i] >> sh) & bm) : 0xFFFFu;
                 const unsigned peers = __match_any_sync(kFull, key);
                 if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[key], static_cast<unsigned>(__popc(peers)));
-            } else if (act) {  // trailing bytes are spread evenly: plain atomics
-                atomicAdd(&hist[key], 1u);
+            }
+        } else {
+            for (int i = tid; i < n; i += kSelNT) {
+                const unsigned v = u[i];
+                if ((v & mask) == prefix) atomicAdd(&hist[(v >> sh) & bm], 1u);
             }
         }
         __syncthreads();
         if (tid < 32) {
-            unsigned c[8], sum = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; sum += c[j]; }
+            constexpr int PER = kSelBins / 32;
+            unsigned sum = 0;
+#pragma unroll 8
+            for (int j = 0; j < PER; ++j) sum += hist[PER * lane + j];
             unsigned incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
             const unsigned excl = incl - sum, want = static_cast<unsigned>(kk);
-            if (excl <= want && want < incl) {   // exactly one lane: the one whose eight bins contain rank kk
+            if (excl <= want && want < incl) {   // exactly one lane: the one whose bins contain rank kk
                 unsigned cum = excl;
-                int bin = 8 * lane;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (cum + c[j] > want) break;
-                    cum += c[j]; ++bin;
+                int bin = PER * lane;
+                for (int j = 0; j < PER; ++j) {
+                    const unsigned c = hist[PER * lane + j];
+                    if (cum + c > want) break;
+                    cum += c; ++bin;
                 }
                 bc[0] = static_cast<unsigned>(bin);
                 bc[1] = cum;
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hist[8 * lane + j] = 0;   // ready for the next pass
         }
         __syncthreads();
         prefix |= bc[0] << sh;
-        mask |= 0xFFu << sh;
+        mask |= bm << sh;
         kk -= static_cast<int>(bc[1]);
+        if (pass < 2) for (int j = tid; j < kSelBins; j += kSelNT) hist[j] = 0;   // ready for the next pass
         __syncthreads();
     }
     kth = prefix;
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(kSelNT, 2) lc_select_kernel(const lc_select_ar
     const int Hn = (d.H + d.sample - 1) / d.sample, Wn = (d.W + d.sample - 1) / d.sample, N = Hn * Wn, HW = d.H * d.W;
     float* vals = reinterpret_cast<float*>(smem_raw);                    // [N] quantile operand
     unsigned char* mflag = reinterpret_cast<unsigned char*>(vals + N);   // [N] segmentation mask of the sampled pixel
-    __shared__ unsigned hist[256];
+    __shared__ unsigned hist[kSelBins];
     __shared__ unsigned bc[4];
     __shared__ float redf[kSelNT / 32 * 2];
     __shared__ int wsum[kSelNT / 32];
