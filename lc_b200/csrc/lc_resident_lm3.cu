@@ -19,14 +19,23 @@ namespace lc {
 
 constexpr int kLm3NT = 128;
 
+// what the solve needs per pose in shared memory (2.4 KB instead of the 15 KB PoseShared of the loss kernels)
+struct LmShared {
+    double K[9], pose[7];
+    double red[(kLm3NT / 32) * 28];
+    double fin[28];
+    unsigned long long tma_bar;
+    LmState lm;
+};
+
 __device__ __forceinline__ float* lm3_points(unsigned char* base) {
-    return reinterpret_cast<float*>(base + ((sizeof(PoseShared) + 15) & ~size_t(15)));
+    return reinterpret_cast<float*>(base + ((sizeof(LmShared) + 15) & ~size_t(15)));
 }
-static size_t lm3_smem_bytes(int n) { return ((sizeof(PoseShared) + 15) & ~size_t(15)) + sizeof(float) * 3 * static_cast<size_t>(round_up4(n)); }
+static size_t lm3_smem_bytes(int n) { return ((sizeof(LmShared) + 15) & ~size_t(15)) + sizeof(float) * 3 * static_cast<size_t>(round_up4(n)); }
 
 // One evaluation pass (cost; with JAC also J'^T J' and J'^T r in the left basis): X from shared memory, x and the weights from L2.
 template <int NT, bool JAC>
-__device__ __forceinline__ void lm3_eval_pass(const lc_args& a, PoseShared& s, const float* A0, const float* A1, const float* A2, int b, int n,
+__device__ __forceinline__ void lm3_eval_pass(const lc_args& a, LmShared& s, const float* A0, const float* A1, const float* A2, int b, int n,
                                               bool sanitize) {
     const LmState& L = s.lm;
     double acc[28];
@@ -89,10 +98,10 @@ __device__ __forceinline__ void lm3_eval_pass(const lc_args& a, PoseShared& s, c
     block_reduce<28, NT>(acc, s.red, s.fin);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 3) lc_lm3_kernel(const lc_args a, int npad, int tma_mask) {
+template <int NT, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS) lc_lm3_kernel(const lc_args a, int npad, int tma_mask) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PoseShared& s = *reinterpret_cast<PoseShared*>(smem_raw);
+    LmShared& s = *reinterpret_cast<LmShared*>(smem_raw);
     float* A0 = lm3_points(smem_raw);
     float* A1 = A0 + npad;
     float* A2 = A1 + npad;
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(NT, 3) lc_lm3_kernel(const lc_args a, int npad
         }
         solved = L.term == TERM_CONVERGENCE;
     }
-    if (tid == 0) lm_write_result<float>(a, s, b, n, solved);
+    if (tid == 0) lm_write_result<float, LmShared>(a, s, b, n, solved);
 }
 
 // A (B,N,C) fp32 view whose component slabs are contiguous and 16-byte aligned for every pose
@@ -175,41 +184,64 @@ static bool lm3_planar(const lc_view& v, int n) {
 
 static std::atomic<int> g_lm3_smem[64];   // opt-in shared memory per block of the device, cached per device index
 
-// Measured (B200, N = 4096, profiles/phase_timing_r2.txt): B = 8192: 1233 vs 1333 us for two 192-thread CTAs per SM (+8 %);
-// B = 1024: 203 vs 198 us (1024 poses are 2.3 waves of 444 slots, the third wave is nearly empty) -> used from B = 2048 on.
-// LC_B200_LM3 = 1 forces it at any batch size (tests), = 0 disables it.
+#ifndef LC_LM3_MIN_BATCH
+#define LC_LM3_MIN_BATCH 2048   // see the measurements at the top of lm3_supported's callers (profiles/phase_timing_r2.txt)
+#endif
+
+// Poses per SM: three (158 registers, no spills).  Four fit in shared memory up to N ~ 4.3k with the 2.4 KB LmShared, but then the
+// threads get 128 registers, the fp64 accumulators spill, and with ~200 KB of the SM's 256 KB configured as shared memory the L1
+// that would absorb the spills is ~25 KB: measured 259 vs 203 us at B = 1024 and 1621 vs 1236 us at B = 8192.  LC_B200_LM_CTAS = 4
+// selects that variant for A/B runs.
+static int lm3_ctas(const lc_args& a, int smem_optin) {
+    if (const char* e = getenv("LC_B200_LM_CTAS")) {
+        if (atoi(e) == 4 && 4 * (lm3_smem_bytes(a.N) + 1024) <= static_cast<size_t>(smem_optin) + 1024) return 4;
+    }
+    return 3;
+}
+static int lm3_optin_smem() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const bool cached = dev >= 0 && dev < 64;
+    if (cached && (v = g_lm3_smem[dev].load(std::memory_order_relaxed)) > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cached) g_lm3_smem[dev].store(v, std::memory_order_relaxed);
+    return v;
+}
+
+// LC_B200_LM3 = 1 forces this kernel at any batch size (tests, A/B runs), = 0 disables it; LC_B200_LM_CTAS = 3 | 4 pins the poses per SM.
 bool lm3_supported(const lc_args& a) {
     const char* e = getenv("LC_B200_LM3");
     if (e && e[0] == '0') return false;
-    if (!(e && e[0] == '1') && a.B < 2048) return false;
     if (a.dtype != LC_F32 || a.N <= 2048) return false;   // N <= 2048: four 128-thread CTAs of the 20 B/point kernel fit already
     if (a.weight_mode != LC_W_ICOV_DIAG && a.weight_mode != LC_W_INV_STD) return false;
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
-    const bool cached = dev >= 0 && dev < 64;
-    if (!(cached && (v = g_lm3_smem[dev].load(std::memory_order_relaxed)) > 0)) {
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) { cudaGetLastError(); return false; }
-        if (cached) g_lm3_smem[dev].store(v, std::memory_order_relaxed);
-    }
+    const int v = lm3_optin_smem();
+    if (v <= 0) return false;
     // three CTAs (+1 KB of system shared memory each) must fit in the SM's shared memory = the per-block opt-in limit + 1 KB
-    return 3 * (lm3_smem_bytes(a.N) + 1024) <= static_cast<size_t>(v) + 1024;
+    if (3 * (lm3_smem_bytes(a.N) + 1024) > static_cast<size_t>(v) + 1024) return false;
+    if (e && e[0] == '1') return true;
+    return a.B >= LC_LM3_MIN_BATCH;
 }
 
-int launch_lm3(const lc_args& a, cudaStream_t st) {
+template <int CTAS>
+static int launch_lm3_t(const lc_args& a, cudaStream_t st, int lim) {
     const size_t smem = lm3_smem_bytes(a.N);
     static std::atomic<bool> configured[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-        const int lim = (dev >= 0 && dev < 64) ? g_lm3_smem[dev].load(std::memory_order_relaxed) : 0;   // filled by lm3_supported
-        const cudaError_t e = cudaFuncSetAttribute(lc_lm3_kernel<kLm3NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim > 0 ? lim : static_cast<int>(smem));
+        const cudaError_t e = cudaFuncSetAttribute(lc_lm3_kernel<kLm3NT, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim > 0 ? lim : static_cast<int>(smem));
         if (e != cudaSuccess) return static_cast<int>(e);
         if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
     }
     const int mask = getenv("LC_B200_NO_TMA") ? 0 : ((lm3_planar(a.pts3d, a.N) ? 1 : 0) | (lm3_planar(a.pts2d, a.N) ? 2 : 0) | (lm3_planar(a.weights, a.N) ? 4 : 0));
-    lc_lm3_kernel<kLm3NT><<<a.B, kLm3NT, smem, st>>>(a, round_up4(a.N), mask);
-    note_kernel("lc::lc_lm3_kernel<%d,LM,X in smem,3 CTAs/SM>", kLm3NT);
+    lc_lm3_kernel<kLm3NT, CTAS><<<a.B, kLm3NT, smem, st>>>(a, round_up4(a.N), mask);
+    note_kernel("lc::lc_lm3_kernel<%d,LM,X in smem,%d CTAs/SM>", kLm3NT, CTAS);
     return static_cast<int>(cudaGetLastError());
+}
+
+int launch_lm3(const lc_args& a, cudaStream_t st) {
+    const int lim = lm3_optin_smem();
+    return lm3_ctas(a, lim) == 4 ? launch_lm3_t<4>(a, st, lim) : launch_lm3_t<3>(a, st, lim);
 }
 
 }  // namespace lc
