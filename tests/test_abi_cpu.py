@@ -142,3 +142,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "cpu_oracle" not in txt and "liblc_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_flag_constants_match_the_header(tmp_path):
+    """The Python mirror of the flag / weight-mode / status enums equals the header's values (compiled with the host gcc)."""
+    c = tmp_path / "fl.c"
+    c.write_text('#include <stdio.h>\n#include "%s"\nint main(){printf("%%d %%d %%d %%d %%d %%d %%d %%d %%d %%d %%d %%d %%d %%d",'
+                 'LC_FLAG_NAN_TO_NUM,LC_FLAG_TOL_NEEDS_SUCCESS,LC_FLAG_EXACT_HESSIAN,LC_FLAG_FORCE_STREAMING,LC_FLAG_LM_MIXED,LC_FLAG_COV_2D,'
+                 'LC_W_ICOV_DIAG,LC_W_ICOV_FULL,LC_W_INV_STD,LC_W_SQRT_L,LC_ST_HESS_NOT_SPD,LC_ST_PRIOR_NOT_GOOD,LC_ST_COV_NOT_GOOD,'
+                 'LC_B200_ABI_VERSION);return 0;}\n' % os.path.join(ROOT, "include", "lc_b200.h"))
+    exe = tmp_path / "fl"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([gcc, "-o", str(exe), str(c)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [nat.FLAG_NAN_TO_NUM, nat.FLAG_TOL_NEEDS_SUCCESS, nat.FLAG_EXACT_HESSIAN, nat.FLAG_FORCE_STREAMING, nat.FLAG_LM_MIXED,
+                   nat.FLAG_COV_2D, nat.W_ICOV_DIAG, nat.W_ICOV_FULL, nat.W_INV_STD, nat.W_SQRT_L, nat.ST_HESS_NOT_SPD,
+                   nat.ST_PRIOR_NOT_GOOD, nat.ST_COV_NOT_GOOD, nat.ABI_VERSION]
