@@ -20,7 +20,7 @@
 
 namespace lc {
 
-// 512 threads x 46 registers: two CTAs per SM (1024 threads allowed one, and B = 256 samples then ran as two waves on 148 SMs)
+// 512 threads x 64 registers: two CTAs per SM (1024 threads allowed one, and B = 256 samples then ran as two waves on 148 SMs)
 constexpr int kSelNT = 512;
 
 __device__ __forceinline__ float sel_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }

@@ -86,7 +86,7 @@ def main():
     nbytes = B * H * W * (3 * 4 + 2 * 4 + 4 + 28)       # xyz + logits + mask in; 28 B per output slot (pts3d, pts2d, inv_cov)
     emit(kernel="lc_select_kernel (f2 point selection)", workload=f"B={B} x {H} x {W}, sample 1, quantile_in_mask, softmax fused",
          us=t * 1e6, algorithmic_bytes=nbytes, GBps=nbytes / t / 1e9, hbm_peak=peak, frac=nbytes / t / 1e9 / peak, peak_source=src,
-         note="logits are read 3x (max, sum, use) and the quantile is a 4-pass radix select in shared memory")
+         note="logits are read twice (max; exp + sum + quantile operand in one pass) and the quantile is a 3-pass radix select in shared memory")
 
     # ---- f3: zebrapose training producer fused with the LC loss (zycbv: B=32, 128x128, sample 3) and a large batch ----
     from lc_b200.dense import dense_loss_fwd_bwd
